@@ -1,0 +1,133 @@
+"""Generate the committed golden fixtures from the LIVE reference (build container only).
+
+Run:  python tests/golden/make_golden.py
+
+Needs /root/reference (read-only) and the numpy stand-in for earthkit-utils under
+oracle/refshim.  Produces, next to this file:
+
+* ref_csv.npz    -- the reference's own golden CSVs (reference tests/data/*.csv, consumed by
+                    reference tests/thermo/test_thermo.py:171-186,206-331,346-356,706-849),
+                    re-packed column by column as float64 (keys "<file stem>/<column>").
+* ref_live.npz   -- inputs and outputs of the unmodified reference functions for every Case of
+                    tests/cases.py on four input sets (seeded random, edge values, the reference's
+                    t_hum_p_data.csv grid, the moist-adiabat grid), float64 and float32.
+* PINNING.json   -- oracle-vs-reference comparison made at generation time (max relative
+                    difference and NaN-position mismatches per case).
+
+Nothing in the GPU tests, smoke() or bench.py reads /root/reference; they read these files.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+sys.path.insert(0, os.path.join(REF, "src"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from earthkit.meteo import thermo as ref_thermo  # noqa: E402  (the live reference)
+
+import thermo_oracle as oracle  # noqa: E402
+from cases import CASES, edge_inputs, random_inputs  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def load_csv(name):
+    d = np.genfromtxt(os.path.join(REF, "tests", "data", name), delimiter=",", names=True)
+    return {k: np.asarray(d[k], dtype=np.float64) for k in d.dtype.names}
+
+
+def pack_csvs():
+    out = {}
+    for name in sorted(os.listdir(os.path.join(REF, "tests", "data"))):
+        if name.endswith(".csv"):
+            for k, v in load_csv(name).items():
+                out[f"{name[:-4]}/{k}"] = v
+    return out
+
+
+def input_sets():
+    csv = load_csv("t_hum_p_data.csv")
+    ma = load_csv("t_on_most_adiabat.csv")
+    n = csv["t"].size
+    rng = np.random.default_rng(3)
+    # the reference grid only carries t, td, r, q, p -- fill the other fields deterministically
+    grid = dict(t=csv["t"], td=csv["td"], r=csv["r"], q=csv["q"], p=csv["p"])
+    grid["tc"] = grid["t"] - 273.16
+    grid["w"] = grid["q"] / (1 - grid["q"])
+    grid["e"] = grid["p"] * grid["q"] / (0.621981 + 0.378019 * grid["q"])
+    grid["es"] = grid["e"] * 100.0 / grid["r"]
+    grid["ept"] = grid["t"] * (1e5 / grid["p"]) ** 0.285691 * np.exp(2488.88 * grid["q"] / grid["td"])
+    grid["th"] = grid["t"] * (1e5 / grid["p"]) ** 0.285691
+    grid["t_def"] = rng.uniform(250.0, 310.0, n)
+    grid["p_def"] = rng.uniform(7e4, 1.05e5, n)
+    madict = random_inputs(ma["ept"].size, seed=11)
+    madict["ept"] = ma["ept"]
+    madict["p"] = ma["p"]
+    return {"rand": random_inputs(1024, seed=0), "edge": edge_inputs(), "grid": grid, "ma": madict}
+
+
+def call(mod, case, inputs, dtype):
+    args = [np.ascontiguousarray(inputs[a].astype(dtype)) for a in case.args]
+    with np.errstate(all="ignore"):
+        res = getattr(mod, case.fn)(*args, **case.kwargs)
+    if not isinstance(res, tuple):
+        res = (res,)
+    return [np.asarray(r) for r in res]
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, "ref_csv.npz"), **pack_csvs())
+
+    sets = input_sets()
+    blob = {}
+    pin = {"numpy": np.__version__, "cases": {}, "summary": {}}
+    worst = 0.0
+    nan_mismatch = 0
+    n_entries = 0
+    for sname, inputs in sets.items():
+        for k, v in inputs.items():
+            blob[f"in/{sname}/{k}"] = v
+        for dtype in (np.float64, np.float32):
+            if dtype is np.float32 and sname in ("grid", "ma"):
+                continue
+            dname = np.dtype(dtype).name
+            for case in CASES:
+                if sname == "ma" and case.fn != "temperature_on_moist_adiabat":
+                    continue
+                r = call(ref_thermo, case, inputs, dtype)
+                o = call(oracle, case, inputs, dtype)
+                for k, (rv, ov) in enumerate(zip(r, o)):
+                    blob[f"out/{sname}/{dname}/{case.id}/{k}"] = rv
+                    assert rv.shape == ov.shape, (case.id, rv.shape, ov.shape)
+                    assert rv.dtype == ov.dtype, (case.id, rv.dtype, ov.dtype)
+                    nm = int(np.sum(np.isnan(rv) != np.isnan(ov)))
+                    fin = np.isfinite(rv) & np.isfinite(ov)
+                    infs = int(np.sum((~fin) & ~np.isnan(rv) & (rv != ov)))
+                    with np.errstate(all="ignore"):
+                        rel = np.abs(rv[fin] - ov[fin]) / np.maximum(np.abs(rv[fin]), 1e-300)
+                    m = float(rel.max()) if rel.size else 0.0
+                    worst = max(worst, m)
+                    nan_mismatch += nm + infs
+                    n_entries += 1
+                    if m > 0.0 or nm or infs:  # only deviations are listed; an empty dict = bit-identical
+                        pin["cases"][f"{sname}/{dname}/{case.id}/{k}"] = {"max_rel": m, "nan_mismatch": nm, "inf_mismatch": infs}
+    pin["summary"] = {"worst_max_rel": worst, "nan_or_inf_mismatches": nan_mismatch, "n_entries": n_entries}
+    np.savez_compressed(os.path.join(HERE, "ref_live.npz"), **blob)
+    with open(os.path.join(HERE, "PINNING.json"), "w") as f:
+        json.dump(pin, f, indent=1, sort_keys=True)
+    print(json.dumps(pin["summary"]))
+
+
+if __name__ == "__main__":
+    main()
