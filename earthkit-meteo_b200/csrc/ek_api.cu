@@ -1,0 +1,148 @@
+// ek_api.cu -- library-level entry points: version, errors, launch configuration, the field partitioner
+// and the host-buffer pipeline.
+#include <cstring>
+#include <vector>
+
+#include "ek_launch.cuh"
+
+namespace ek {
+
+std::atomic<int> g_threads{256};
+std::atomic<int> g_ctas_per_sm{16};
+std::atomic<uint64_t> g_launches{0};
+
+static thread_local char t_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int sm_count_current_device() {
+    static std::atomic<int> cache[64];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return -1;
+    if (dev < 64) {
+        int v = cache[dev].load(std::memory_order_relaxed);
+        if (v > 0) return v;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
+
+}  // namespace ek
+
+using namespace ek;
+
+extern "C" EK_EXPORT int ek_thermo_version(void) { return EK_THERMO_VERSION; }
+extern "C" EK_EXPORT const char* ek_thermo_last_error(void) { return t_err; }
+extern "C" EK_EXPORT uint64_t ek_thermo_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" EK_EXPORT int ek_thermo_set_launch_config(int threads, int ctas_per_sm) {
+    if (threads != 0) {
+        if (threads < 32 || threads > EK_MAX_THREADS || threads % 32) return set_error(EK_ERR_ARG, "threads=%d must be a multiple of 32 in [32, %d]", threads, EK_MAX_THREADS);
+        g_threads.store(threads);
+    }
+    if (ctas_per_sm != 0) {
+        if (ctas_per_sm < 1 || ctas_per_sm > 4096) return set_error(EK_ERR_ARG, "ctas_per_sm=%d out of range", ctas_per_sm);
+        g_ctas_per_sm.store(ctas_per_sm);
+    }
+    return EK_OK;
+}
+
+// Contiguous, aligned shards of a flat index range: the first (units % world) ranks get
+// one extra unit of `align` points; the last shard absorbs the sub-unit remainder.
+extern "C" EK_EXPORT int ek_thermo_shard_range(int64_t n, int world, int rank, int64_t align, int64_t* begin, int64_t* end) {
+    if (n < 0 || world < 1 || rank < 0 || rank >= world || align < 1 || !begin || !end)
+        return set_error(EK_ERR_ARG, "shard_range: bad arguments n=%lld world=%d rank=%d align=%lld", (long long)n, world, rank, (long long)align);
+    const int64_t units = n / align;
+    const int64_t base = units / world, extra = units % world;
+    const int64_t b = (rank * base + (rank < extra ? rank : extra)) * align;
+    int64_t e = b + (base + (rank < extra ? 1 : 0)) * align;
+    if (rank == world - 1) e = n;
+    *begin = b;
+    *end = e;
+    return EK_OK;
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------------
+namespace {
+struct StreamSet {
+    std::vector<cudaStream_t> s;
+    ~StreamSet() {
+        for (auto st : s) cudaStreamDestroy(st);
+    }
+};
+}  // namespace
+
+template <typename T>
+static int impl_host_suite(int kind, const void* h_a, const void* h_b, const void* h_c, void* const* h_outs, uint32_t out_mask, int64_t n,
+                           void* workspace, size_t workspace_bytes, int n_slots) {
+    if (kind != 0 && kind != 1) return set_error(EK_ERR_ENUM, "host_suite: kind=%d", kind);
+    if (!h_a || !h_b || !h_c || !h_outs || !workspace) return set_error(EK_ERR_ARG, "host_suite: NULL buffer");
+    if (n < 0 || n_slots < 1 || n_slots > 16) return set_error(EK_ERR_ARG, "host_suite: n=%lld n_slots=%d", (long long)n, n_slots);
+    if (out_mask == 0 || out_mask >= (1u << S_NSLOTS)) return set_error(EK_ERR_ARG, "host_suite: out_mask=0x%x", out_mask);
+    int n_out = 0;
+    for (int k = 0; k < S_NSLOTS; ++k)
+        if ((out_mask >> k) & 1u) {
+            if (!h_outs[k]) return set_error(EK_ERR_ARG, "host_suite: output %d requested but its buffer is NULL", k);
+            ++n_out;
+        }
+    if (n == 0) return EK_OK;
+    if (!aligned16(workspace)) return set_error(EK_ERR_ARG, "host_suite: workspace must be 16-byte aligned");
+    const int n_arr = 3 + n_out;
+    int64_t chunk = (int64_t)(workspace_bytes / ((size_t)n_slots * n_arr * sizeof(T)));
+    chunk -= chunk % 4096;  // keeps every sub-buffer 16-byte aligned and tiles whole
+    if (chunk <= 0) return set_error(EK_ERR_PIPE, "host_suite: workspace of %zu bytes is too small for %d slots", workspace_bytes, n_slots);
+    if (chunk > n) chunk = ((n + 4095) / 4096) * 4096;
+
+    StreamSet ss;
+    for (int i = 0; i < n_slots; ++i) {
+        cudaStream_t st;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return set_error((int)e, "host_suite: cudaStreamCreate: %s", cudaGetErrorString(e));
+        ss.s.push_back(st);
+    }
+    const T* hin[3] = {static_cast<const T*>(h_a), static_cast<const T*>(h_b), static_cast<const T*>(h_c)};
+    T* ws = static_cast<T*>(workspace);
+    int64_t done = 0;
+    for (int64_t c = 0; done < n; ++c, done += chunk) {
+        const int slot = (int)(c % n_slots);
+        cudaStream_t st = ss.s[slot];
+        const int64_t m = (n - done) < chunk ? (n - done) : chunk;
+        T* base = ws + (int64_t)slot * n_arr * chunk;
+        ek_operand ins[3];
+        for (int k = 0; k < 3; ++k) {
+            T* d = base + (int64_t)k * chunk;
+            cudaError_t e = cudaMemcpyAsync(d, hin[k] + done, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return set_error((int)e, "host_suite: H2D copy: %s", cudaGetErrorString(e));
+            ins[k].ptr = d;
+            ins[k].value = 0.0;
+        }
+        void* douts[S_NSLOTS];
+        int j = 0;
+        for (int k = 0; k < S_NSLOTS; ++k) douts[k] = ((out_mask >> k) & 1u) ? (void*)(base + (int64_t)(3 + j++) * chunk) : nullptr;
+        int rc = kind == 0 ? launch<OpSuiteTQP, T>("host_suite", ins, douts, m, Params{}, st)
+                           : launch<OpSuiteTTdP, T>("host_suite", ins, douts, m, Params{}, st);
+        if (rc != EK_OK) return rc;
+        for (int k = 0; k < S_NSLOTS; ++k)
+            if (douts[k]) {
+                cudaError_t e = cudaMemcpyAsync(static_cast<T*>(h_outs[k]) + done, douts[k], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) return set_error((int)e, "host_suite: D2H copy: %s", cudaGetErrorString(e));
+            }
+    }
+    for (auto st : ss.s) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return set_error((int)e, "host_suite: stream sync: %s", cudaGetErrorString(e));
+    }
+    return EK_OK;
+}
+EK_API(host_suite,
+       (int kind, const void* h_a, const void* h_b, const void* h_c, void* const* h_outs, uint32_t out_mask, int64_t n, void* workspace,
+        size_t workspace_bytes, int n_slots),
+       (kind, h_a, h_b, h_c, h_outs, out_mask, n, workspace, workspace_bytes, n_slots))

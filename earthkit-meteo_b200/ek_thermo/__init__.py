@@ -1,0 +1,15 @@
+"""ek_thermo -- B200-native (sm_100a) kernels for the earthkit-meteo thermo hot path.
+
+    from ek_thermo import thermo          # drop-in for `from earthkit.meteo import thermo` on CUDA tensors
+    theta = thermo.potential_temperature(t, p)
+
+    from ek_thermo import fused            # one pass, many outputs
+    fields = fused.suite_tqp(t, q, p)      # {"theta", "es", "rh", "td", "tv"}
+
+Importing this package loads libek_thermo.so and fails loudly if it has not been built: there is no
+CPU or eager-PyTorch fallback anywhere.
+"""
+from . import _backend, fused, hostpipe, partition, thermo  # noqa: F401
+from ._backend import EkThermoError, launch_count, set_launch_config, version  # noqa: F401
+
+__all__ = ["thermo", "fused", "partition", "hostpipe", "version", "launch_count", "set_launch_config", "EkThermoError"]

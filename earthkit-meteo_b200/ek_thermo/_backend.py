@@ -1,0 +1,265 @@
+"""ctypes binding of libek_thermo.so and the generic "launch one entry point" helper.
+
+PyTorch is used for tensor handles, allocation and streams only.  There is NO CPU path: if the
+shared library is missing, or an argument is not a CUDA tensor, the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = os.environ.get("EK_THERMO_LIB", "libek_thermo.so")
+LIB_PATH = LIB_NAME if os.path.isabs(LIB_NAME) else os.path.join(_HERE, LIB_NAME)
+
+
+class ek_operand(ctypes.Structure):
+    """Mirror of ``struct ek_operand`` (include/ek_thermo.h): device pointer or broadcast scalar."""
+
+    _fields_ = [("ptr", c_void_p), ("value", c_double)]
+
+
+class EkThermoError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"ek_thermo: CUDA library {LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C earthkit-meteo_b200/csrc`. There is no CPU fallback."
+    )
+_lib = ctypes.CDLL(LIB_PATH)
+_lib.ek_thermo_version.restype = c_int
+_lib.ek_thermo_last_error.restype = ctypes.c_char_p
+_lib.ek_thermo_launch_count.restype = c_uint64
+_lib.ek_thermo_set_launch_config.argtypes = [c_int, c_int]
+_lib.ek_thermo_shard_range.argtypes = [c_int64, c_int, c_int, c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
+
+_SUFFIX = {torch.float64: "f64", torch.float32: "f32"}
+
+# option kinds of every entry point, in C argument order:  operands..., options..., outputs..., n, stream
+# name -> (n_inputs, option ctypes, n_outputs)
+SIGNATURES = {
+    "celsius_to_kelvin": (1, (), 1),
+    "kelvin_to_celsius": (1, (), 1),
+    "specific_humidity_from_mixing_ratio": (1, (), 1),
+    "mixing_ratio_from_specific_humidity": (1, (), 1),
+    "vapour_pressure_from_specific_humidity": (2, (), 1),
+    "vapour_pressure_from_mixing_ratio": (2, (), 1),
+    "specific_humidity_from_vapour_pressure": (2, (c_double,), 1),
+    "mixing_ratio_from_vapour_pressure": (2, (c_double,), 1),
+    "saturation_vapour_pressure": (1, (c_int,), 1),
+    "saturation_vapour_pressure_slope": (1, (c_int,), 1),
+    "saturation_mixing_ratio": (2, (c_int,), 1),
+    "saturation_specific_humidity": (2, (c_int,), 1),
+    "saturation_mixing_ratio_slope": (4, (c_int, c_int, c_int, c_double), 1),
+    "saturation_specific_humidity_slope": (4, (c_int, c_int, c_int, c_double), 1),
+    "temperature_from_saturation_vapour_pressure": (1, (), 1),
+    "relative_humidity_from_dewpoint": (2, (), 1),
+    "relative_humidity_from_specific_humidity": (3, (), 1),
+    "specific_humidity_from_dewpoint": (2, (), 1),
+    "mixing_ratio_from_dewpoint": (2, (), 1),
+    "specific_humidity_from_relative_humidity": (3, (), 1),
+    "dewpoint_from_relative_humidity": (2, (), 1),
+    "dewpoint_from_specific_humidity": (2, (), 1),
+    "virtual_temperature": (2, (), 1),
+    "virtual_potential_temperature": (3, (), 1),
+    "potential_temperature": (2, (), 1),
+    "temperature_from_potential_temperature": (2, (), 1),
+    "pressure_on_dry_adiabat": (3, (), 1),
+    "temperature_on_dry_adiabat": (3, (), 1),
+    "lcl_temperature": (2, (c_int,), 1),
+    "lcl": (3, (c_int,), 2),
+    "specific_gas_constant": (1, (), 1),
+    "ept_from_dewpoint": (3, (c_int,), 1),
+    "ept_from_specific_humidity": (3, (c_int,), 1),
+    "saturation_ept": (2, (c_int,), 1),
+    "temperature_on_moist_adiabat": (2, (c_int, c_int), 1),
+    "wet_bulb_temperature_from_dewpoint": (3, (c_int, c_int), 1),
+    "wet_bulb_temperature_from_specific_humidity": (3, (c_int, c_int), 1),
+    "wet_bulb_potential_temperature_from_dewpoint": (3, (c_int, c_int), 1),
+    "wet_bulb_potential_temperature_from_specific_humidity": (3, (c_int, c_int), 1),
+    "ept_wet_bulb": (3, (c_int, c_int, c_int, c_int), 2),
+}
+
+for _name, (_nin, _opts, _nout) in SIGNATURES.items():
+    for _sfx in ("f64", "f32"):
+        _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
+        _fn.argtypes = [ek_operand] * _nin + list(_opts) + [c_void_p] * _nout + [c_int64, c_void_p]
+        _fn.restype = c_int
+for _name in ("suite_tqp", "suite_ttdp"):
+    for _sfx in ("f64", "f32"):
+        _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
+        _fn.argtypes = [ek_operand] * 3 + [ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p]
+        _fn.restype = c_int
+for _sfx in ("f64", "f32"):
+    _fn = getattr(_lib, f"ek_thermo_host_suite_{_sfx}")
+    _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p, c_size_t, c_int]
+    _fn.restype = c_int
+
+
+def version() -> int:
+    return int(_lib.ek_thermo_version())
+
+
+def launch_count() -> int:
+    """Kernels launched by the library since it was loaded."""
+    return int(_lib.ek_thermo_launch_count())
+
+
+def set_launch_config(threads: int = 0, ctas_per_sm: int = 0) -> None:
+    _check(_lib.ek_thermo_set_launch_config(threads, ctas_per_sm))
+
+
+def _check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = (_lib.ek_thermo_last_error() or b"").decode()
+    if rc == -3:  # EK_ERR_EPS: the reference raises ValueError (T:189-190)
+        raise ValueError(msg)
+    if rc < 0:
+        raise ValueError(f"ek_thermo: {msg} (code {rc})")
+    raise EkThermoError(f"ek_thermo: {msg} (cudaError {rc})")
+
+
+# ----------------------------------------------------------------------------------------------
+# argument preparation
+# ----------------------------------------------------------------------------------------------
+def _check_device(tensors):
+    """Every array argument must be a CUDA tensor on one device.  No CPU path exists."""
+    dev = None
+    for t in tensors:
+        if not t.is_cuda:
+            raise TypeError(
+                "ek_thermo: got a CPU tensor. This package only runs on CUDA tensors (no CPU fallback); "
+                "use earthkit.meteo.thermo for host arrays."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"ek_thermo: tensors are on different devices ({dev} and {t.device})")
+    return dev
+
+
+def _prepare(args):
+    """Split positional array-likes into (tensors | python scalars), find dtype, device, broadcast shape."""
+    items = []
+    tensors = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            items.append(a)
+            tensors.append(a)
+        elif isinstance(a, (int, float)) and not isinstance(a, bool):
+            items.append(float(a))
+        elif a is None:
+            items.append(None)
+        else:
+            raise TypeError(
+                f"ek_thermo: unsupported argument type {type(a).__name__}; expected torch CUDA tensors or Python numbers "
+                "(numpy / host arrays are served by earthkit.meteo.thermo, there is no CPU path here)"
+            )
+    if not tensors:
+        raise TypeError("ek_thermo: at least one argument must be a torch CUDA tensor")
+    dev = _check_device(tensors)
+    dtype = tensors[0].dtype
+    for t in tensors[1:]:
+        dtype = torch.promote_types(dtype, t.dtype)
+    if dtype not in _SUFFIX:
+        dtype = torch.float64 if not dtype.is_floating_point else (torch.float32 if dtype in (torch.float16, torch.bfloat16) else dtype)
+    shape = torch.broadcast_shapes(*[t.shape for t in tensors])
+    n = 1
+    for s in shape:
+        n *= int(s)
+    ops = []
+    keep = []
+    for it in items:
+        if it is None:
+            ops.append(ek_operand(None, 0.0))
+        elif isinstance(it, float):
+            ops.append(ek_operand(None, it))
+        else:
+            t = it
+            if t.numel() == 1 and n > 1:
+                ops.append(ek_operand(None, float(t.item())))  # broadcast by value, never materialised
+                continue
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            if t.shape != shape:
+                t = t.expand(shape)
+            if not t.is_contiguous():
+                t = t.contiguous()
+            keep.append(t)
+            ops.append(ek_operand(t.data_ptr(), 0.0))
+    return ops, keep, dtype, dev, shape, n
+
+
+def _call(symbol: str, dtype, device, c_args):
+    """The one place where the C ABI is entered.  (Tests patch this to check the host logic on CPU.)"""
+    fn = getattr(_lib, f"ek_thermo_{symbol}_{_SUFFIX[dtype]}")
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _check(fn(*c_args, c_void_p(stream)))
+
+
+def _empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def execute(symbol: str, args, options=(), want=None):
+    """Run entry point `symbol` on positional array args; returns a tensor or a tuple of tensors.
+
+    `want` optionally selects which outputs to allocate (tuple of bools), for the two-output kernels.
+    """
+    nin, opt_types, nout = SIGNATURES[symbol]
+    assert len(args) == nin and len(options) == len(opt_types), symbol
+    ops, keep, dtype, dev, shape, n = _prepare(args)
+    if want is None:
+        want = (True,) * nout
+    outs = [_empty(shape, dtype, dev) if w else None for w in want]
+    c_args = list(ops) + [ct(v) for ct, v in zip(opt_types, options)]
+    c_args += [c_void_p(o.data_ptr()) if o is not None else c_void_p(None) for o in outs]
+    c_args.append(c_int64(n))
+    _call(symbol, dtype, dev, c_args)
+    del keep
+    res = tuple(o for o in outs if o is not None)
+    return res[0] if len(res) == 1 else res
+
+
+def execute_suite(symbol: str, args, out_names, slots, out=None):
+    """Run a fused suite; `slots` are the output slot numbers wanted; returns {name: tensor}."""
+    ops, keep, dtype, dev, shape, n = _prepare(args)
+    ptrs = (c_void_p * 8)()
+    mask = 0
+    res = {}
+    for name, k in zip(out_names, slots):
+        if out is not None and name in out:
+            t = out[name]
+            if t.dtype != dtype or t.shape != shape or not t.is_contiguous() or t.device != dev:
+                raise ValueError(f"ek_thermo: preallocated output {name!r} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+        else:
+            t = _empty(shape, dtype, dev)
+        res[name] = t
+        ptrs[k] = t.data_ptr()
+        mask |= 1 << k
+    c_args = list(ops) + [ctypes.cast(ptrs, ctypes.POINTER(c_void_p)), c_uint32(mask), c_int64(n)]
+    _call(symbol, dtype, dev, c_args)
+    del keep
+    return res
+
+
+def shard_range(n: int, world: int, rank: int, align: int = 1):
+    b, e = c_int64(0), c_int64(0)
+    _check(_lib.ek_thermo_shard_range(n, world, rank, align, ctypes.byref(b), ctypes.byref(e)))
+    return int(b.value), int(e.value)
+
+
+def host_suite(kind: int, dtype, h_ptrs, h_out_ptrs, mask: int, n: int, workspace: torch.Tensor, n_slots: int):
+    fn = getattr(_lib, f"ek_thermo_host_suite_{_SUFFIX[dtype]}")
+    outs = (c_void_p * 8)(*h_out_ptrs)
+    with torch.cuda.device(workspace.device):
+        _check(fn(kind, c_void_p(h_ptrs[0]), c_void_p(h_ptrs[1]), c_void_p(h_ptrs[2]), ctypes.cast(outs, ctypes.POINTER(c_void_p)),
+                  c_uint32(mask), c_int64(n), c_void_p(workspace.data_ptr()), c_size_t(workspace.numel() * workspace.element_size()),
+                  c_int(n_slots)))

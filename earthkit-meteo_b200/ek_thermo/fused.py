@@ -1,0 +1,79 @@
+"""Fused multi-output kernels: read the state of each grid point once, write every requested field.
+
+These have no counterpart function in the reference; every output equals the reference function
+named in ``SUITE_TQP_OUTPUTS`` / ``SUITE_TTDP_OUTPUTS`` applied to the same inputs (the oracle's
+``suite_tqp`` / ``suite_ttdp`` state that composition).  HBM traffic per point is
+``8 * (3 + len(outputs))`` bytes in float64, instead of one full read+write pass per function.
+"""
+from __future__ import annotations
+
+from . import _backend as _b
+
+# output name -> slot (include/ek_thermo.h EK_S_*), with the reference function each one equals
+SUITE_TQP_OUTPUTS = {
+    "theta": 0,  # potential_temperature(t, p)                          T:801-829
+    "es": 1,  # saturation_vapour_pressure(t)                            T:235-279
+    "rh": 2,  # relative_humidity_from_specific_humidity(t, q, p)        T:524-556
+    "td": 3,  # dewpoint_from_specific_humidity(q, p)                    T:702-735
+    "tv": 4,  # virtual_temperature(t, q)                                T:738-764
+    "w": 5,  # mixing_ratio_from_specific_humidity(q)                    T:80-102
+    "e": 6,  # vapour_pressure_from_specific_humidity(q, p)              T:105-131
+    "thetav": 7,  # virtual_potential_temperature(t, q, p)               T:767-798
+}
+SUITE_TTDP_OUTPUTS = {
+    "theta": 0,  # potential_temperature(t, p)
+    "es": 1,  # saturation_vapour_pressure(t)
+    "rh": 2,  # relative_humidity_from_dewpoint(t, td)                   T:494-521
+    "q": 3,  # specific_humidity_from_dewpoint(td, p)                    T:559-591
+    "tv": 4,  # virtual_temperature(t, q(td, p))
+    "w": 5,  # mixing_ratio_from_dewpoint(td, p)                         T:594-626
+    "e": 6,  # saturation_vapour_pressure(td, phase="water")
+    "thetav": 7,  # virtual_potential_temperature(t, q(td, p), p)
+}
+DEFAULT_TQP = ("theta", "es", "rh", "td", "tv")
+DEFAULT_TTDP = ("theta", "es", "rh", "q", "tv")
+
+_EPT = {"ifs": 0, "bolton35": 1, "bolton39": 2}
+_TM = {None: 0, "none": 0, "direct": 1, "bisect": 2, "newton": 3}
+
+
+def _slots(table, outputs):
+    try:
+        return [table[o] for o in outputs]
+    except KeyError as e:
+        raise ValueError(f"unknown suite output {e.args[0]!r}; choose from {sorted(table)}") from None
+
+
+def suite_tqp(t, q, p, outputs=DEFAULT_TQP, out=None):
+    """One pass over (t, q, p) producing the requested fields; returns ``{name: tensor}``."""
+    outputs = tuple(outputs)
+    return _b.execute_suite("suite_tqp", (t, q, p), outputs, _slots(SUITE_TQP_OUTPUTS, outputs), out)
+
+
+def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None):
+    """One pass over (t, td, p) producing the requested fields; returns ``{name: tensor}``."""
+    outputs = tuple(outputs)
+    return _b.execute_suite("suite_ttdp", (t, td, p), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out)
+
+
+def ept_wet_bulb(t, h, p, humidity="q", ept_method="ifs", t_method="direct", potential=True, want_ept=True, want_wb=True):
+    """Equivalent potential temperature and wet-bulb (potential) temperature in one pass.
+
+    ``h`` is the specific humidity (``humidity="q"``) or the dewpoint (``"td"``).  Equals
+    ``ept_from_*`` and ``wet_bulb[_potential]_temperature_from_*`` of the reference with the same
+    ``ept_method`` / ``t_method``.  Returns ``(ept, wb)``, with None for an output not wanted.
+    """
+    if humidity not in ("q", "td"):
+        raise ValueError(f"humidity={humidity!r} must be 'q' or 'td'")
+    m = _EPT[ept_method]
+    if t_method not in _TM or (t_method == "direct" and not potential):
+        raise ValueError(f"temperature_on_moist_adiabat: invalid t_method={t_method} specified!")
+    tm = _TM[t_method]
+    if tm == 0:
+        want_wb = False
+    if not (want_ept or want_wb):
+        raise ValueError("nothing to compute")
+    res = _b.execute("ept_wet_bulb", (t, h, p), (int(humidity == "q"), m, tm, int(bool(potential))), want=(want_ept, want_wb))
+    if want_ept and want_wb:
+        return res
+    return (res, None) if want_ept else (None, res)

@@ -1,0 +1,58 @@
+"""Host-buffer front end: the fused suite over numpy / host arrays, streamed through the GPU.
+
+This is the "reference-facing" call measured as ``e2e`` by bench.py: inputs and outputs live in HOST
+memory; the C library overlaps H2D copies, the suite kernel and D2H copies of successive chunks on
+several streams (ek_thermo_host_suite_*).  All arithmetic still happens on the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _backend as _b
+from .fused import DEFAULT_TQP, DEFAULT_TTDP, SUITE_TQP_OUTPUTS, SUITE_TTDP_OUTPUTS
+
+_TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
+
+
+def pinned_empty(n, dtype=np.float64):
+    """A page-locked host array (numpy view of a pinned torch tensor), for full-speed PCIe copies."""
+    t = torch.empty(int(n), dtype=_TORCH[np.dtype(dtype)], pin_memory=True)
+    a = t.numpy()
+    a.flags.writeable = True
+    return a
+
+
+class HostSuite:
+    """Reusable pipeline: owns the device workspace (allocated once through torch) and the stream slots."""
+
+    def __init__(self, device="cuda:0", workspace_bytes=1 << 30, n_slots=3):
+        self.device = torch.device(device)
+        self.n_slots = int(n_slots)
+        self.workspace = torch.empty(int(workspace_bytes), dtype=torch.uint8, device=self.device)
+
+    def _run(self, kind, table, a, b, c, outputs, out):
+        arrs = [np.ascontiguousarray(x) for x in (a, b, c)]
+        dt = arrs[0].dtype
+        if dt not in _TORCH or any(x.dtype != dt or x.shape != arrs[0].shape for x in arrs):
+            raise TypeError("host suite: the three inputs must be float64 or float32 numpy arrays of one shape")
+        n = arrs[0].size
+        ptrs = [0] * 8
+        mask = 0
+        res = {}
+        for name in outputs:
+            k = table[name]
+            o = out[name] if out is not None and name in out else np.empty(arrs[0].shape, dtype=dt)
+            if o.dtype != dt or o.size != n or not o.flags.c_contiguous:
+                raise ValueError(f"host suite: output {name!r} must be a contiguous {dt} array of {n} elements")
+            res[name] = o
+            ptrs[k] = o.ctypes.data
+            mask |= 1 << k
+        _b.host_suite(kind, _TORCH[dt], [x.ctypes.data for x in arrs], ptrs, mask, n, self.workspace, self.n_slots)
+        return res
+
+    def suite_tqp(self, t, q, p, outputs=DEFAULT_TQP, out=None):
+        return self._run(0, SUITE_TQP_OUTPUTS, t, q, p, tuple(outputs), out)
+
+    def suite_ttdp(self, t, td, p, outputs=DEFAULT_TTDP, out=None):
+        return self._run(1, SUITE_TTDP_OUTPUTS, t, td, p, tuple(outputs), out)

@@ -1,0 +1,153 @@
+/* ek_thermo.h -- C ABI of libek_thermo.so: B200 (sm_100a) kernels for the earthkit-meteo thermo hot path.
+ *
+ * The reference (ecmwf/earthkit-meteo) has no FFI: its boundary for this path is the Python function
+ * namespace earthkit.meteo.thermo.array.* (src/earthkit/meteo/thermo/array/thermo.py = "T" below,
+ * es_comp.py = "E").  Each entry point here replaces the body of one of those functions for device
+ * arrays; the Python drop-in (earthkit-meteo_b200/ek_thermo/thermo.py) binds them with ctypes and keeps
+ * the reference's names, argument order, defaults and exceptions.  INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *  - every array argument is a DEVICE pointer to n contiguous elements of the function's dtype
+ *    (suffix _f64 = double, _f32 = float); only natural alignment is required (16-byte aligned
+ *    pointers take the 128-bit load/store path, others a scalar path inside the same kernel);
+ *  - an input may instead be a broadcast scalar: ek_operand{NULL, value};
+ *  - the caller allocates and owns every buffer; the library never allocates, frees or synchronises;
+ *  - the launch is asynchronous on `stream` (a cudaStream_t / CUstream, NULL = default stream) of the
+ *    CURRENT device; the caller selects the device;
+ *  - return 0 on success, a positive cudaError_t if the launch failed, or a negative EK_ERR_* code for
+ *    argument errors (ek_thermo_last_error() gives the text, thread-local);
+ *  - numerical failures are in-band NaN, exactly where the reference produces NaN;
+ *  - thread-safe and re-entrant; no CPU fallback exists anywhere in the library.
+ */
+#ifndef EK_THERMO_H
+#define EK_THERMO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EK_THERMO_VERSION 100 /* 0.1.0 */
+
+typedef struct ek_operand {
+    const void* ptr; /* device pointer, or NULL for a broadcast scalar */
+    double value;    /* the scalar when ptr == NULL (rounded to the dtype once, as numpy does) */
+} ek_operand;
+
+enum { EK_OK = 0, EK_ERR_ARG = -1, EK_ERR_ENUM = -2, EK_ERR_EPS = -3, EK_ERR_PIPE = -4 };
+
+/* option enums (strings of the reference API -> ints) */
+enum { EK_PHASE_MIXED = 0, EK_PHASE_WATER = 1, EK_PHASE_ICE = 2 };            /* E:22 */
+enum { EK_LCL_DAVIES = 0, EK_LCL_BOLTON = 1 };                                /* T:960-968 */
+enum { EK_EPT_IFS = 0, EK_EPT_BOLTON35 = 1, EK_EPT_BOLTON39 = 2 };            /* T:1319-1323 */
+enum { EK_TM_NONE = 0, EK_TM_DIRECT = 1, EK_TM_BISECT = 2, EK_TM_NEWTON = 3 }; /* T:1504-1509, T:1631 */
+enum { EK_HUM_DEWPOINT = 0, EK_HUM_SPECIFIC = 1 };
+
+/* output slots of the fused suites (bit k of out_mask <-> outs[k]) */
+enum {
+    EK_S_THETA = 0, EK_S_ES = 1, EK_S_RH = 2, EK_S_TD_OR_Q = 3, EK_S_TV = 4, EK_S_W = 5, EK_S_E = 6, EK_S_THETAV = 7,
+    EK_S_NSLOTS = 8
+};
+
+/* declares ek_thermo_<name>_f64 and ek_thermo_<name>_f32 with the same parameter list */
+#define EK_THERMO_FN(name, ...)              \
+    int ek_thermo_##name##_f64(__VA_ARGS__); \
+    int ek_thermo_##name##_f32(__VA_ARGS__);
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ek_thermo_version(void);
+const char* ek_thermo_last_error(void);
+/* threads per CTA (multiple of 32, <= 1024) and CTAs per SM used to size grids; 0 keeps the default */
+int ek_thermo_set_launch_config(int threads, int ctas_per_sm);
+/* number of kernels this library has launched since load (all threads) */
+uint64_t ek_thermo_launch_count(void);
+/* field partitioner: contiguous shard [begin,end) of rank `rank` of `world` over n points, edges
+ * aligned to `align` points; returns EK_ERR_ARG on bad arguments */
+int ek_thermo_shard_range(int64_t n, int world, int rank, int64_t align, int64_t* begin, int64_t* end);
+
+/* ---- simple conversions ---------------------------------------------------------------------- */
+EK_THERMO_FN(celsius_to_kelvin, ek_operand t, void* out, int64_t n, void* stream)                    /* T:21-35 */
+EK_THERMO_FN(kelvin_to_celsius, ek_operand t, void* out, int64_t n, void* stream)                    /* T:38-52 */
+EK_THERMO_FN(specific_humidity_from_mixing_ratio, ek_operand w, void* out, int64_t n, void* stream)  /* T:55-77 */
+EK_THERMO_FN(mixing_ratio_from_specific_humidity, ek_operand q, void* out, int64_t n, void* stream)  /* T:80-102 */
+EK_THERMO_FN(vapour_pressure_from_specific_humidity, ek_operand q, ek_operand p, void* out, int64_t n, void* stream) /* T:105-131 */
+EK_THERMO_FN(vapour_pressure_from_mixing_ratio, ek_operand w, ek_operand p, void* out, int64_t n, void* stream)      /* T:134-159 */
+/* eps <= 0 -> EK_ERR_EPS (reference: ValueError, T:189-190 / T:226-227) */
+EK_THERMO_FN(specific_humidity_from_vapour_pressure, ek_operand e, ek_operand p, double eps, void* out, int64_t n, void* stream) /* T:162-196 */
+EK_THERMO_FN(mixing_ratio_from_vapour_pressure, ek_operand e, ek_operand p, double eps, void* out, int64_t n, void* stream)      /* T:199-232 */
+
+/* ---- saturation vapour pressure and friends -------------------------------------------------- */
+EK_THERMO_FN(saturation_vapour_pressure, ek_operand t, int phase, void* out, int64_t n, void* stream)                 /* T:235-279, E:31-79 */
+EK_THERMO_FN(saturation_vapour_pressure_slope, ek_operand t, int phase, void* out, int64_t n, void* stream)           /* T:344-364, E:82-106 */
+EK_THERMO_FN(saturation_mixing_ratio, ek_operand t, ek_operand p, int phase, void* out, int64_t n, void* stream)      /* T:282-310 */
+EK_THERMO_FN(saturation_specific_humidity, ek_operand t, ek_operand p, int phase, void* out, int64_t n, void* stream) /* T:313-341 */
+/* es / es_slope are optional precomputed inputs: pass has_es / has_es_slope = 0 to have them computed (T:407-410) */
+EK_THERMO_FN(saturation_mixing_ratio_slope, ek_operand t, ek_operand p, ek_operand es, ek_operand es_slope, int has_es,
+             int has_es_slope, int phase, double eps, void* out, int64_t n, void* stream)                             /* T:367-415 */
+EK_THERMO_FN(saturation_specific_humidity_slope, ek_operand t, ek_operand p, ek_operand es, ek_operand es_slope, int has_es,
+             int has_es_slope, int phase, double eps, void* out, int64_t n, void* stream)                             /* T:418-467 */
+EK_THERMO_FN(temperature_from_saturation_vapour_pressure, ek_operand es, void* out, int64_t n, void* stream)          /* T:470-491, E:109-130 */
+
+/* ---- humidity / dewpoint conversions ---------------------------------------------------------- */
+EK_THERMO_FN(relative_humidity_from_dewpoint, ek_operand t, ek_operand td, void* out, int64_t n, void* stream)                     /* T:494-521 */
+EK_THERMO_FN(relative_humidity_from_specific_humidity, ek_operand t, ek_operand q, ek_operand p, void* out, int64_t n, void* stream) /* T:524-556 */
+EK_THERMO_FN(specific_humidity_from_dewpoint, ek_operand td, ek_operand p, void* out, int64_t n, void* stream)                     /* T:559-591 */
+EK_THERMO_FN(mixing_ratio_from_dewpoint, ek_operand td, ek_operand p, void* out, int64_t n, void* stream)                          /* T:594-626 */
+EK_THERMO_FN(specific_humidity_from_relative_humidity, ek_operand t, ek_operand r, ek_operand p, void* out, int64_t n, void* stream) /* T:629-663 */
+EK_THERMO_FN(dewpoint_from_relative_humidity, ek_operand t, ek_operand r, void* out, int64_t n, void* stream)                      /* T:666-699 */
+EK_THERMO_FN(dewpoint_from_specific_humidity, ek_operand q, ek_operand p, void* out, int64_t n, void* stream)                      /* T:702-735 */
+
+/* ---- virtual / potential temperature, dry adiabats, lcl ----------------------------------------- */
+EK_THERMO_FN(virtual_temperature, ek_operand t, ek_operand q, void* out, int64_t n, void* stream)                          /* T:738-764 */
+EK_THERMO_FN(virtual_potential_temperature, ek_operand t, ek_operand q, ek_operand p, void* out, int64_t n, void* stream)  /* T:767-798 */
+EK_THERMO_FN(potential_temperature, ek_operand t, ek_operand p, void* out, int64_t n, void* stream)                        /* T:801-829 */
+EK_THERMO_FN(temperature_from_potential_temperature, ek_operand th, ek_operand p, void* out, int64_t n, void* stream)      /* T:832-858 */
+EK_THERMO_FN(pressure_on_dry_adiabat, ek_operand t, ek_operand t_def, ek_operand p_def, void* out, int64_t n, void* stream) /* T:861-889 */
+EK_THERMO_FN(temperature_on_dry_adiabat, ek_operand p, ek_operand t_def, ek_operand p_def, void* out, int64_t n, void* stream) /* T:892-920 */
+EK_THERMO_FN(lcl_temperature, ek_operand t, ek_operand td, int method, void* out, int64_t n, void* stream)                 /* T:923-968 */
+EK_THERMO_FN(lcl, ek_operand t, ek_operand td, ek_operand p, int method, void* t_lcl_out, void* p_lcl_out, int64_t n, void* stream) /* T:971-1000 */
+EK_THERMO_FN(specific_gas_constant, ek_operand q, void* out, int64_t n, void* stream)                                      /* T:1678-1707 */
+
+/* ---- equivalent potential temperature, moist adiabats, wet bulb -------------------------------- */
+EK_THERMO_FN(ept_from_dewpoint, ek_operand t, ek_operand td, ek_operand p, int method, void* out, int64_t n, void* stream)          /* T:1326-1387 */
+EK_THERMO_FN(ept_from_specific_humidity, ek_operand t, ek_operand q, ek_operand p, int method, void* out, int64_t n, void* stream)  /* T:1390-1415 */
+EK_THERMO_FN(saturation_ept, ek_operand t, ek_operand p, int method, void* out, int64_t n, void* stream)                            /* T:1418-1469 */
+/* t_method: EK_TM_BISECT or EK_TM_NEWTON */
+EK_THERMO_FN(temperature_on_moist_adiabat, ek_operand ept, ek_operand p, int ept_method, int t_method, void* out, int64_t n, void* stream) /* T:1472-1509 */
+EK_THERMO_FN(wet_bulb_temperature_from_dewpoint, ek_operand t, ek_operand td, ek_operand p, int ept_method, int t_method, void* out,
+             int64_t n, void* stream)                                                                                                /* T:1512-1549 */
+EK_THERMO_FN(wet_bulb_temperature_from_specific_humidity, ek_operand t, ek_operand q, ek_operand p, int ept_method, int t_method,
+             void* out, int64_t n, void* stream)                                                                                     /* T:1552-1590 */
+/* t_method: EK_TM_DIRECT, EK_TM_BISECT or EK_TM_NEWTON */
+EK_THERMO_FN(wet_bulb_potential_temperature_from_dewpoint, ek_operand t, ek_operand td, ek_operand p, int ept_method, int t_method,
+             void* out, int64_t n, void* stream)                                                                                     /* T:1593-1634 */
+EK_THERMO_FN(wet_bulb_potential_temperature_from_specific_humidity, ek_operand t, ek_operand q, ek_operand p, int ept_method,
+             int t_method, void* out, int64_t n, void* stream)                                                                       /* T:1637-1675 */
+
+/* ---- fused multi-output kernels (new in this build; each output equals the reference function named
+ *      at its slot, see EK_S_*) ------------------------------------------------------------------- */
+/* (t, q, p) -> any subset of {theta, es, rh, td, tv, w, e, thetav}; outs[k] may be NULL when bit k is clear */
+EK_THERMO_FN(suite_tqp, ek_operand t, ek_operand q, ek_operand p, void* const* outs, uint32_t out_mask, int64_t n, void* stream)
+/* (t, td, p) -> any subset of {theta, es, rh, q, tv, w, e, thetav} */
+EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t out_mask, int64_t n, void* stream)
+/* (t, h, p) -> ept and/or the wet-bulb (potential) temperature in one pass.  h is td or q (humidity_kind),
+ * at_p0 = 1 gives the wet-bulb POTENTIAL temperature; either output pointer may be NULL (but not both);
+ * t_method EK_TM_NONE computes ept only */
+EK_THERMO_FN(ept_wet_bulb, ek_operand t, ek_operand h, ek_operand p, int humidity_kind, int ept_method, int t_method, int at_p0,
+             void* ept_out, void* wb_out, int64_t n, void* stream)
+
+/* ---- host-buffer pipeline: the same suite kernel fed from HOST arrays ---------------------------------
+ * Streams n points through the GPU in chunks: H2D copy, kernel and D2H copy of successive chunks overlap on
+ * `n_slots` internal streams.  Host buffers should be page-locked for full PCIe speed.  `workspace` is a
+ * caller-owned DEVICE buffer of workspace_bytes; chunk size = workspace_bytes / (n_slots * (3 + popcount(mask)) * sizeof(T)).
+ * Blocks until every output byte is in host memory.  kind: 0 = suite_tqp, 1 = suite_ttdp. */
+EK_THERMO_FN(host_suite, int kind, const void* h_a, const void* h_b, const void* h_c, void* const* h_outs, uint32_t out_mask,
+             int64_t n, void* workspace, size_t workspace_bytes, int n_slots)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EK_THERMO_H */

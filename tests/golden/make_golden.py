@@ -11,6 +11,7 @@ oracle/refshim.  Produces, next to this file:
 * ref_live.npz   -- inputs and outputs of the unmodified reference functions for every Case of
                     tests/cases.py on four input sets (seeded random, edge values, the reference's
                     t_hum_p_data.csv grid, the moist-adiabat grid), float64 and float32.
+* ifs_l137_ab.npz -- the IFS L137 A/B half-level coefficients from the reference's conf JSON (bench input layout).
 * PINNING.json   -- oracle-vs-reference comparison made at generation time (max relative
                     difference and NaN-position mismatches per case).
 
@@ -86,8 +87,17 @@ def call(mod, case, inputs, dtype):
     return [np.asarray(r) for r in res]
 
 
+def pack_ifs_levels():
+    """IFS L137 hybrid A/B half-level coefficients (reference src/earthkit/meteo/conf/ifs_levels_conf.json),
+    used by bench.py to lay out the synthetic O1280 x 137 pressure field."""
+    with open(os.path.join(REF, "src", "earthkit", "meteo", "conf", "ifs_levels_conf.json")) as f:
+        d = json.load(f)["137"]
+    return {"A": np.asarray(d["A"], dtype=np.float64), "B": np.asarray(d["B"], dtype=np.float64)}
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "ref_csv.npz"), **pack_csvs())
+    np.savez_compressed(os.path.join(HERE, "ifs_l137_ab.npz"), **pack_ifs_levels())
 
     sets = input_sets()
     blob = {}

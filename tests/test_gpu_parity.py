@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path, called through the C ABI by the drop-in package, against the oracle
+on identical inputs, against the committed live-reference fixtures, the reference's golden CSVs and its
+inline known-answer vectors.  Run on the B200 box with ``pytest -m gpu``.
+"""
+import numpy as np
+import pytest
+import torch
+
+import thermo_oracle as oracle
+from cases import CASES, edge_inputs, random_inputs
+from compare import compare
+from kat import KATS
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ek():
+    import ek_thermo
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return ek_thermo
+
+
+def _to_dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a.astype(dtype))).to(DEV)
+
+
+def _run_case(ek, case, inputs, dtype):
+    args_np = [np.ascontiguousarray(inputs[a].astype(dtype)) for a in case.args]
+    before = ek.launch_count()
+    res = getattr(ek.thermo, case.fn)(*[torch.from_numpy(a).to(DEV) for a in args_np], **case.kwargs)
+    assert ek.launch_count() == before + 1, "exactly one kernel launch per call"
+    with np.errstate(all="ignore"):
+        want = getattr(oracle, case.fn)(*args_np, **case.kwargs)
+    if not isinstance(res, tuple):
+        res, want = (res,), (want,)
+    return [r.cpu().numpy() for r in res], want
+
+
+# N chosen so that the vector body (several tiles), the scalar tail and a ragged end are all exercised
+N_RANDOM = 256 * 4 * 37 + 77
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_cuda_matches_oracle_random(ek, case, dtype):
+    got, want = _run_case(ek, case, random_inputs(N_RANDOM, seed=5), dtype)
+    for g, w in zip(got, want):
+        compare(case, g, w, dtype)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_cuda_matches_oracle_edge(ek, case, dtype):
+    with np.errstate(all="ignore"):
+        got, want = _run_case(ek, case, edge_inputs(n=4099, seed=21), dtype)
+    for g, w in zip(got, want):
+        compare(case, g, w, dtype, edge=True)
+
+
+@pytest.mark.parametrize("sname,dname", [("rand", "float64"), ("edge", "float64"), ("grid", "float64"), ("ma", "float64"),
+                                         ("rand", "float32")])
+def test_cuda_matches_live_reference_fixtures(ek, ref_live, sname, dname):
+    """Outputs of the unmodified reference (tests/golden/make_golden.py) -- independent of the oracle."""
+    dtype = np.dtype(dname).type
+    pre = f"in/{sname}/"
+    inputs = {k[len(pre):]: v for k, v in ref_live.items() if k.startswith(pre)}
+    n = 0
+    for case in CASES:
+        if f"out/{sname}/{dname}/{case.id}/0" not in ref_live:
+            continue
+        res = getattr(ek.thermo, case.fn)(*[_to_dev(inputs[a], dtype) for a in case.args], **case.kwargs)
+        res = res if isinstance(res, tuple) else (res,)
+        for k, r in enumerate(res):
+            compare(case, r.cpu().numpy(), ref_live[f"out/{sname}/{dname}/{case.id}/{k}"], dtype, edge=(sname == "edge"))
+            n += 1
+    assert n > 50 or sname == "ma"
+
+
+@pytest.mark.parametrize("kat", KATS, ids=[f"{i}-{k[0]}" for i, k in enumerate(KATS)])
+def test_kat_reference_numbers(ek, kat):
+    fn, args, kwargs, expected, rtol = kat
+    got = getattr(ek.thermo, fn)(*[torch.tensor(a, dtype=torch.float64, device=DEV) for a in args], **kwargs)
+    if not isinstance(got, tuple):
+        got, expected = (got,), (expected,)
+    for g, e in zip(got, expected):
+        np.testing.assert_allclose(g.cpu().numpy(), np.asarray(e, dtype=np.float64), rtol=rtol, atol=1e-8, equal_nan=True)
+
+
+# ---- the reference's golden CSVs with the reference tests' own tolerances (TT:169-356, 706-849) ----
+def test_csv_goldens(ek, ref_csv):
+    th = ek.thermo
+    d = lambda k: torch.from_numpy(ref_csv[k]).to(DEV)  # noqa: E731
+    close = lambda a, b, **kw: np.testing.assert_allclose(a.cpu().numpy(), ref_csv[b], equal_nan=True, **kw)  # noqa: E731
+    for ph in ("mixed", "water", "ice"):
+        close(th.saturation_vapour_pressure(d("sat_vp/t"), phase=ph), f"sat_vp/{ph}", rtol=1e-12)
+        close(th.saturation_vapour_pressure_slope(d("sat_vp_slope/t"), phase=ph), f"sat_vp_slope/{ph}", rtol=1e-12)
+        close(th.saturation_mixing_ratio(d("sat_mr/t"), d("sat_mr/p"), phase=ph), f"sat_mr/{ph}", rtol=1e-12)
+        close(th.saturation_specific_humidity(d("sat_q/t"), d("sat_q/p"), phase=ph), f"sat_q/{ph}", rtol=1e-12)
+        close(th.saturation_mixing_ratio_slope(d("sat_mr_slope/t"), d("sat_mr_slope/p"), phase=ph), f"sat_mr_slope/{ph}", rtol=1e-12)
+        close(th.saturation_specific_humidity_slope(d("sat_q_slope/t"), d("sat_q_slope/p"), phase=ph), f"sat_q_slope/{ph}", rtol=1e-12)
+    t, td, q, p = (d(f"t_hum_p_data/{k}") for k in ("t", "td", "q", "p"))
+    for m in ("ifs", "bolton35", "bolton39"):
+        close(th.ept_from_dewpoint(t, td, p, method=m), f"eqpt/{m}_td", rtol=1e-12)
+        close(th.ept_from_specific_humidity(t, q, p, method=m), f"eqpt/{m}_q", rtol=1e-12)
+        close(th.saturation_ept(t, p, method=m), f"seqpt/{m}", rtol=1e-12)
+        for tm in ("bisect", "newton"):
+            rt = 1e-3 if tm == "bisect" else 1e-10
+            close(th.temperature_on_moist_adiabat(d("t_on_most_adiabat/ept"), d("t_on_most_adiabat/p"), ept_method=m, t_method=tm),
+                  f"t_on_most_adiabat/{m}_{tm}", rtol=rt, atol=0)
+            close(th.wet_bulb_temperature_from_dewpoint(t, td, p, ept_method=m, t_method=tm), f"t_wet/{m}_{tm}_td", rtol=rt, atol=0)
+            close(th.wet_bulb_temperature_from_specific_humidity(t, q, p, ept_method=m, t_method=tm), f"t_wet/{m}_{tm}_q", rtol=rt, atol=0)
+        for tm in ("bisect", "newton", "direct"):
+            rt = 1e-3 if tm == "bisect" else 1e-10
+            close(th.wet_bulb_potential_temperature_from_dewpoint(t, td, p, ept_method=m, t_method=tm), f"t_wetpt/{m}_{tm}_td", rtol=rt, atol=0)
+            close(th.wet_bulb_potential_temperature_from_specific_humidity(t, q, p, ept_method=m, t_method=tm), f"t_wetpt/{m}_{tm}_q", rtol=rt, atol=0)
+
+
+# ---- calling conventions ------------------------------------------------------------------------
+def test_scalar_broadcast_unaligned_nd_noncontiguous(ek):
+    th = ek.thermo
+    inp = random_inputs(50021, seed=9)
+    t, p, q = (torch.from_numpy(inp[k]).to(DEV) for k in ("t", "p", "q"))
+    want = oracle.potential_temperature(inp["t"], 85000.0)
+    np.testing.assert_allclose(th.potential_temperature(t, 85000.0).cpu().numpy(), want, rtol=1e-12)  # python scalar p (TT:622)
+    np.testing.assert_allclose(th.potential_temperature(t, torch.tensor(85000.0, device=DEV, dtype=torch.float64)).cpu().numpy(), want, rtol=1e-12)
+    # unaligned views: pointers offset by one element (8 bytes) take the scalar ld/st path
+    want = oracle.relative_humidity_from_specific_humidity(inp["t"][1:], inp["q"][1:], inp["p"][1:])
+    np.testing.assert_allclose(th.relative_humidity_from_specific_humidity(t[1:], q[1:], p[1:]).cpu().numpy(), want, rtol=1e-12)
+    want = oracle.potential_temperature(inp["t"][:-1], inp["p"][1:])
+    np.testing.assert_allclose(th.potential_temperature(t[:-1], p[1:]).cpu().numpy(), want, rtol=1e-12)
+    # N-D and non-contiguous
+    t2, p2 = t[:50000].reshape(50, 1000), p[:50000].reshape(50, 1000)
+    got = th.potential_temperature(t2.t(), p2.t())
+    assert got.shape == (1000, 50)
+    np.testing.assert_allclose(got.cpu().numpy(), oracle.potential_temperature(inp["t"][:50000].reshape(50, 1000).T, inp["p"][:50000].reshape(50, 1000).T), rtol=1e-12)
+    # broadcasting a per-level pressure column against a [level, point] field
+    pl = p[:50].reshape(50, 1)
+    got = th.potential_temperature(t2, pl)
+    np.testing.assert_allclose(got.cpu().numpy(), oracle.potential_temperature(inp["t"][:50000].reshape(50, 1000), inp["p"][:50].reshape(50, 1)), rtol=1e-12)
+    # N-D through the iterative solvers (a superset of the reference, which is 1-D only there)
+    e2 = torch.from_numpy(inp["ept"][:50000]).to(DEV).reshape(50, 1000)
+    got = th.temperature_on_moist_adiabat(e2, p2, t_method="newton")
+    np.testing.assert_allclose(got.cpu().numpy().ravel(), oracle.temperature_on_moist_adiabat(inp["ept"][:50000], inp["p"][:50000], t_method="newton"),
+                               rtol=1e-10, equal_nan=True)
+    # empty input
+    assert th.potential_temperature(t[:0], p[:0]).numel() == 0
+    # optional precomputed es / es_slope
+    es = th.saturation_vapour_pressure(t)
+    des = th.saturation_vapour_pressure_slope(t)
+    a = th.saturation_mixing_ratio_slope(t, p)
+    b = th.saturation_mixing_ratio_slope(t, p, es=es, es_slope=des)
+    assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+    # float32 in -> float32 out; mixed dtypes promote
+    assert th.potential_temperature(t.float(), p.float()).dtype == torch.float32
+    assert th.potential_temperature(t.float(), p).dtype == torch.float64
+
+
+def test_error_conventions(ek):
+    th = ek.thermo
+    t = torch.full((8,), 280.0, device=DEV, dtype=torch.float64)
+    with pytest.raises(ValueError):
+        th.specific_humidity_from_vapour_pressure(t, t, eps=0)  # T:189-190
+    with pytest.raises(ValueError):
+        th.saturation_mixing_ratio_slope(t, t, eps=-1.0)  # T:405-406
+    with pytest.raises(ValueError):
+        th.lcl_temperature(t, t, method="x")  # T:968
+    with pytest.raises(KeyError):
+        th.ept_from_dewpoint(t, t, t, method="x")  # T:1026
+    with pytest.raises(ValueError):
+        th.temperature_on_moist_adiabat(t, t, t_method="x")  # T:1509
+    with pytest.raises(ValueError):
+        th.wet_bulb_temperature_from_dewpoint(t, t, t, t_method="direct")
+    assert th.saturation_vapour_pressure(t, phase="x") is None  # E:74-79
+    with pytest.raises(TypeError):
+        th.potential_temperature(t.cpu(), t.cpu())  # no CPU path
+    with pytest.raises(TypeError):
+        th.potential_temperature(np.ones(4), np.ones(4))
+    # inputs are never modified
+    t0 = t.clone()
+    th.saturation_vapour_pressure(t)
+    assert torch.equal(t, t0)
+
+
+# ---- fused suites ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_fused_suites_match_oracle(ek, dtype):
+    from ek_thermo import fused
+
+    inp = random_inputs(N_RANDOM, seed=13)
+    a = {k: np.ascontiguousarray(inp[k].astype(dtype)) for k in ("t", "q", "td", "p")}
+    d = {k: torch.from_numpy(v).to(DEV) for k, v in a.items()}
+    f32 = dtype == np.float32
+    rtol = 2e-5 if f32 else 1e-12
+
+    def check(got, want, names):
+        for name in names:
+            g = got[name].cpu().numpy().astype(np.float64)
+            w = np.asarray(want[name]).astype(np.float64)
+            np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg=name)
+            fin = np.isfinite(w)
+            rel = np.abs(g[fin] - w[fin]) / np.maximum(np.abs(w[fin]), 1e-300)
+            assert np.mean(rel > rtol) <= (0.01 if f32 else 0.0), (name, rel.max())
+
+    before = ek.launch_count()
+    got = fused.suite_tqp(d["t"], d["q"], d["p"], outputs=tuple(fused.SUITE_TQP_OUTPUTS))
+    assert ek.launch_count() == before + 1
+    with np.errstate(all="ignore"):
+        check(got, oracle.suite_tqp(a["t"], a["q"], a["p"]), fused.SUITE_TQP_OUTPUTS)
+        got = fused.suite_ttdp(d["t"], d["td"], d["p"], outputs=tuple(fused.SUITE_TTDP_OUTPUTS))
+        check(got, oracle.suite_ttdp(a["t"], a["td"], a["p"]), fused.SUITE_TTDP_OUTPUTS)
+    # every subset of outputs gives bit-identical fields to the full run (the mask only skips work)
+    full = fused.suite_tqp(d["t"], d["q"], d["p"], outputs=tuple(fused.SUITE_TQP_OUTPUTS))
+    for names in (("theta",), ("rh",), ("td", "tv"), ("theta", "rh"), fused.DEFAULT_TQP, ("w", "e", "thetav")):
+        part = fused.suite_tqp(d["t"], d["q"], d["p"], outputs=names)
+        assert set(part) == set(names)
+        for nme in names:
+            assert torch.equal(torch.nan_to_num(part[nme]), torch.nan_to_num(full[nme])), nme
+    # scalar pressure (a pressure level) and preallocated outputs
+    out = {"theta": torch.empty_like(d["t"])}
+    r = fused.suite_tqp(d["t"], d["q"], 85000.0, outputs=("theta", "rh"), out=out)
+    assert r["theta"].data_ptr() == out["theta"].data_ptr()
+    np.testing.assert_allclose(r["theta"].cpu().numpy().astype(np.float64), oracle.potential_temperature(a["t"], dtype(85000.0)).astype(np.float64), rtol=rtol)
+
+
+@pytest.mark.parametrize("ept_method", ["ifs", "bolton35", "bolton39"])
+@pytest.mark.parametrize("t_method", ["direct", "newton", "bisect"])
+def test_fused_ept_wet_bulb_equals_separate_calls(ek, ept_method, t_method):
+    from ek_thermo import fused
+
+    inp = random_inputs(20011, seed=17)
+    t, q, td, p = (torch.from_numpy(inp[k]).to(DEV) for k in ("t", "q", "td", "p"))
+    for hum, h in (("q", q), ("td", td)):
+        ept, wb = fused.ept_wet_bulb(t, h, p, humidity=hum, ept_method=ept_method, t_method=t_method, potential=True)
+        sfx = "specific_humidity" if hum == "q" else "dewpoint"
+        e1 = getattr(ek.thermo, f"ept_from_{sfx}")(t, h, p, method=ept_method)
+        w1 = getattr(ek.thermo, f"wet_bulb_potential_temperature_from_{sfx}")(t, h, p, ept_method=ept_method, t_method=t_method)
+        assert torch.equal(torch.nan_to_num(ept), torch.nan_to_num(e1))
+        assert torch.equal(torch.nan_to_num(wb), torch.nan_to_num(w1))
+
+
+# ---- full-size properties (BASELINE.json configs[1]: O1280 x 137 levels, float64) -----------------
+def test_full_size_o1280_x137_properties(ek):
+    """At 904 156 160 points the oracle cannot run in full; check size-independent properties instead:
+    (i) the fused outputs equal the single-function kernels bit for bit over the whole field,
+    (ii) a strided sample of 2e5 points equals the oracle, (iii) kelvin<->celsius and theta<->t round trips."""
+    from ek_thermo import fused
+
+    n = 6599680 * 137
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~65 GB of free HBM")
+    g = torch.Generator(device=DEV).manual_seed(0)
+    t = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(200.0, 320.0, generator=g)
+    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e3, 1.05e5, generator=g)
+    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
+    out = fused.suite_tqp(t, q, p)
+    idx = torch.arange(0, n, 4513, device=DEV)
+    ts, qs, ps = (x[idx].cpu().numpy() for x in (t, q, p))
+    with np.errstate(all="ignore"):
+        want = oracle.suite_tqp(ts, qs, ps)
+    for name in fused.DEFAULT_TQP:
+        np.testing.assert_allclose(out[name][idx].cpu().numpy(), want[name], rtol=1e-12, equal_nan=True, err_msg=name)
+    singles = {
+        "theta": lambda: ek.thermo.potential_temperature(t, p),
+        "es": lambda: ek.thermo.saturation_vapour_pressure(t),
+        "rh": lambda: ek.thermo.relative_humidity_from_specific_humidity(t, q, p),
+        "td": lambda: ek.thermo.dewpoint_from_specific_humidity(q, p),
+        "tv": lambda: ek.thermo.virtual_temperature(t, q),
+    }
+    for name, fn in singles.items():
+        one = fn()
+        same = (one == out[name]) | (torch.isnan(one) & torch.isnan(out[name]))
+        assert bool(same.all()), name
+        del one, same
+    th = out["theta"]
+    back = ek.thermo.temperature_from_potential_temperature(th, p)
+    assert float(((back - t).abs() / t).max()) < 1e-13
+    del back
+    c = ek.thermo.kelvin_to_celsius(t)
+    k2 = ek.thermo.celsius_to_kelvin(c)
+    assert float((k2 - t).abs().max()) < 1e-12
+
+
+# ---- host-buffer pipeline and partitioner -----------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_host_pipeline_equals_device_path(ek, dtype):
+    from ek_thermo import fused, hostpipe
+
+    n = 3_000_017
+    inp = random_inputs(n, seed=23)
+    hs = hostpipe.HostSuite(DEV, workspace_bytes=64 << 20, n_slots=3)  # small workspace -> many chunks
+    host = {}
+    for k in ("t", "q", "td", "p"):
+        host[k] = hostpipe.pinned_empty(n, dtype)
+        host[k][:] = inp[k]
+    res = hs.suite_tqp(host["t"], host["q"], host["p"])
+    dev = fused.suite_tqp(*(torch.from_numpy(host[k]).to(DEV) for k in ("t", "q", "p")))
+    for name in fused.DEFAULT_TQP:
+        np.testing.assert_array_equal(res[name], dev[name].cpu().numpy(), err_msg=name)
+    res = hs.suite_ttdp(host["t"], host["td"], host["p"], outputs=("rh", "q"))
+    dev = fused.suite_ttdp(*(torch.from_numpy(host[k]).to(DEV) for k in ("t", "td", "p")), outputs=("rh", "q"))
+    for name in ("rh", "q"):
+        np.testing.assert_array_equal(res[name], dev[name].cpu().numpy(), err_msg=name)
+
+
+def test_sharded_run_equals_single_run(ek):
+    """The partitioner's shards, run one by one on this GPU, reproduce the unsharded result exactly."""
+    from ek_thermo import fused, partition
+
+    n = 1_661_440 * 3 + 5
+    inp = random_inputs(n, seed=29)
+    t, q, p = (torch.from_numpy(inp[k]).to(DEV) for k in ("t", "q", "p"))
+    whole = fused.suite_tqp(t, q, p)
+    for world in (2, 8):
+        parts = {k: [] for k in fused.DEFAULT_TQP}
+        for r in range(world):
+            b, e = partition.shard_range(n, world, r, align=2048)
+            o = fused.suite_tqp(t[b:e], q[b:e], p[b:e])
+            for k in parts:
+                parts[k].append(o[k])
+        for k in parts:
+            cat = torch.cat(parts[k])
+            assert torch.equal(torch.nan_to_num(cat), torch.nan_to_num(whole[k])), k
