@@ -222,7 +222,8 @@ def execute(symbol: str, args, options=(), want=None):
     c_args = list(ops) + [ct(v) for ct, v in zip(opt_types, options)]
     c_args += [c_void_p(o.data_ptr()) if o is not None else c_void_p(None) for o in outs]
     c_args.append(c_int64(n))
-    _call(symbol, dtype, dev, c_args)
+    if n > 0:  # empty in -> empty out, nothing to launch (empty tensors have a NULL data_ptr)
+        _call(symbol, dtype, dev, c_args)
     del keep
     res = tuple(o for o in outs if o is not None)
     return res[0] if len(res) == 1 else res
@@ -245,7 +246,8 @@ def execute_suite(symbol: str, args, out_names, slots, out=None):
         ptrs[k] = t.data_ptr()
         mask |= 1 << k
     c_args = list(ops) + [ctypes.cast(ptrs, ctypes.POINTER(c_void_p)), c_uint32(mask), c_int64(n)]
-    _call(symbol, dtype, dev, c_args)
+    if n > 0:
+        _call(symbol, dtype, dev, c_args)
     del keep
     return res
 

@@ -18,9 +18,7 @@ _TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32
 def pinned_empty(n, dtype=np.float64):
     """A page-locked host array (numpy view of a pinned torch tensor), for full-speed PCIe copies."""
     t = torch.empty(int(n), dtype=_TORCH[np.dtype(dtype)], pin_memory=True)
-    a = t.numpy()
-    a.flags.writeable = True
-    return a
+    return t.numpy()
 
 
 class HostSuite:

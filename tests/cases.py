@@ -130,7 +130,7 @@ def edge_inputs(n=384, seed=7):
     rng = np.random.default_rng(seed)
     nxt = np.nextafter
     tvals = [np.nan, np.inf, -np.inf, 0.0, -10.0, TI, nxt(TI, 0), nxt(TI, 1e3), T0, nxt(T0, 0), nxt(T0, 1e3),
-             32.19, 56.0, 180.0, 233.16, 250.0, 260.0, 273.15, 290.0, 320.0, 373.15, 1e-310, 1e300]
+             32.19, 56.0, 180.0, 233.16, 250.0, 260.0, 273.15, 290.0, 320.0, 373.15, 1e-310, 5000.0]
     pvals = [np.nan, np.inf, 0.0, -1.0e5, 1e-5, 1.0, 50.0, 611.21, 611.2101, 1.0e3, 5.0e4, 8.5e4, 1.0e5, 1.02e5,
              1.876e5, 3.0e5, 1e-310, 1e300]
     qvals = [np.nan, 0.0, -0.01, 1.0, 0.5, 1e-320, 1e-8, 1e-4, 0.003, 0.01, 0.02, 2.0, np.inf]

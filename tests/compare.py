@@ -8,42 +8,81 @@ tie: such points are counted and bounded, all others must agr
 import numpy as np
 
 
-def compare(case, got, want, dtype, edge=False):
+def conditioning(case, args_np, k_out=0):
+    """Relative change of the oracle output when each input moves by one ulp of its dtype (max over inputs).
+
+    A result that differs from the oracle by no more than a 1-ulp input perturbation does is as exact as the
+    formula allows: e.g. theta(t, p - es) loses digits without bound as p - es -> 0, for ANY two correctly
+    rounded exp implementations.  compare() accepts max(rtol, 4 x this) per point."""
+    import thermo_oracle as oracle
+
+    fn = getattr(oracle, case.fn)
+    with np.errstate(all="ignore"):
+        base = fn(*args_np, **case.kwargs)
+        base = np.asarray(base[k_out] if isinstance(base, tuple) else base).astype(np.float64)
+        cond = np.zeros(base.shape)
+        for i, a in enumerate(args_np):
+            pert = list(args_np)
+            pert[i] = np.nextafter(a, np.asarray(np.inf, dtype=a.dtype))
+            r = fn(*pert, **case.kwargs)
+            r = np.asarray(r[k_out] if isinstance(r, tuple) else r).astype(np.float64)
+            d = np.abs(r - base) / np.maximum(np.abs(base), 1e-300)
+            cond = np.fmax(cond, np.where(np.isfinite(d), d, 0.0))
+    return cond
+
+
+DT_LAST = 120.0 / 2 ** 12  # last bisection step, 0.0293 K (T:1069-1075)
+
+
+def compare(case, got, want, dtype, edge=False, cond=None, grid=False):
+    """Assert `got` (new build) equals `want` (oracle / reference) under the parity rule of this module.
+
+    edge: the special-value input set (looser conditioning factor, float32 overflow boundaries tolerated);
+    grid: the reference's own grid-aligned test data, which hits exact bisection sign ties (SURVEY.md 7.3-H3:
+          the reference re-run against its own t_wet.csv already differs by 2.1e-4 relative there).
+    """
     got = np.asarray(got)
     want = np.asarray(want)
     assert got.shape == want.shape, case.id
     f32 = dtype == np.float32
-    if f32:
-        want = want.astype(np.float64)
-        got = got.astype(np.float64)
+    got = got.astype(np.float64)
+    want = want.astype(np.float64)
     nan_g, nan_w = np.isnan(got), np.isnan(want)
-    if case.iterative == "bisect" or f32:
-        # float32 values near overflow/underflow boundaries: a 1-ulp difference decides inf vs finite (and the
-        # reference's float32 "direct" path evaluates its polynomials in float64, SURVEY.md §8(c) caveat)
-        assert np.mean(nan_g != nan_w) < 0.02, case.id
+    bisect = case.iterative == "bisect"
+    if f32:
+        # float32 near overflow/underflow: a 1-ulp difference decides inf vs finite vs NaN, and the reference's
+        # float32 "direct" path evaluates its polynomials in float64 (SURVEY.md 8(c) caveat)
+        nonfin_g, nonfin_w = ~np.isfinite(got), ~np.isfinite(want)
+        assert np.mean(nonfin_g != nonfin_w) < 0.02, f"non-finite positions differ: {case.id}"
+        fin = ~(nonfin_g | nonfin_w)
     else:
-        np.testing.assert_array_equal(nan_g, nan_w, err_msg=f"NaN positions differ: {case.id}")
-    ok = ~(nan_g | nan_w)
-    inf = ok & (np.isinf(got) | np.isinf(want))
-    fin = ok & ~inf
-    if not (f32 and edge):
+        if bisect:
+            assert np.mean(nan_g != nan_w) < 0.02, f"NaN positions differ: {case.id}"
+        else:
+            np.testing.assert_array_equal(nan_g, nan_w, err_msg=f"NaN positions differ: {case.id}")
+        ok = ~(nan_g | nan_w)
+        inf = ok & (np.isinf(got) | np.isinf(want))
+        fin = ok & ~inf
         np.testing.assert_array_equal(got[inf], want[inf], err_msg=f"inf differ: {case.id}")
     rtol = 2e-5 if f32 else 1e-12
     if case.iterative == "newton":
         rtol = 5e-5 if f32 else 1e-10
     with np.errstate(all="ignore"):
-        rel = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)
-        small = np.abs(got[fin] - want[fin]) <= (1e-30 if not f32 else 1e-37)
-    bad = (rel > rtol) & ~small
-    if case.iterative == "bisect":
-        assert bad.mean() < (0.03 if f32 else 0.005), f"{case.id}: {bad.sum()} of {bad.size} bisect points differ"
-    elif f32 and edge:
-        assert bad.mean() < 0.03, f"{case.id}: {bad.sum()} of {bad.size}"
+        diff = np.abs(got[fin] - want[fin])
+        rel = diff / np.maximum(np.abs(want[fin]), 1e-300)
+    # edge set: results that are ~0 by cancellation (e.g. the inverse es formula at t -> 0) carry absolute noise
+    small = diff <= ((1e-6 if f32 else 1e-10) if edge else (1e-37 if f32 else 1e-30))
+    tol = rtol if cond is None else np.maximum(rtol, (32.0 if edge else 4.0) * np.asarray(cond)[fin])
+    bad = (rel > tol) & ~small
+    if bisect:
+        # a flipped sign at a near-tie is pulled back by the remaining halvings: never further than 2 last steps
+        lim = 2.1 * DT_LAST * (4.0 if f32 else 1.0)
+        far = bad & (diff > lim) & (np.abs(want[fin]) < 1e4)
+        assert far.mean() < (0.02 if (f32 or edge) else 0.0) + 1e-12, f"{case.id}: {far.sum()} of {far.size} bisect points off by more than {lim:.3f} K"
+        frac = 0.05 if (grid or f32 or edge) else 0.005
+        assert bad.mean() < frac, f"{case.id}: {bad.sum()} of {bad.size} bisect points differ"
     elif f32:
-        # float32: 1e-5-class agreement, except where the formula itself is ill-conditioned in float32
-        # (p - es -> 0 amplifies a 1-ulp difference of expf without bound): allow 1 % such points
-        assert bad.mean() < 0.01, f"{case.id}: {bad.sum()} of {bad.size} beyond {rtol}"
+        # float32: 1e-5-class agreement; allow 1 % of points where float32 itself is ill-conditioned
+        assert bad.mean() < (0.03 if edge else 0.01), f"{case.id}: {bad.sum()} of {bad.size} beyond {rtol}"
     else:
-        assert not bad.any(), f"{case.id}: max rel {rel.max():.3e} at {np.argmax(rel)}"
-
-
+        assert not bad.any(), f"{case.id}: max rel {rel[bad].max():.3e} at {np.flatnonzero(fin)[np.argmax(np.where(bad, rel, 0))]}"

@@ -13,7 +13,7 @@ import torch
 import hostmath_backend
 import thermo_oracle as oracle
 from cases import CASES, edge_inputs, random_inputs
-from compare import compare
+from compare import compare, conditioning
 from kat import KATS
 
 
@@ -32,16 +32,17 @@ def _run_case(thermo, case, inputs, dtype):
     want = getattr(oracle, case.fn)(*args_np, **case.kwargs)
     if not isinstance(res, tuple):
         res, want = (res,), (want,)
-    return [r.numpy() for r in res], want
+    conds = [None if case.iterative else conditioning(case, args_np, k) for k in range(len(res))]
+    return [r.numpy() for r in res], want, conds
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
 def test_functors_match_oracle_random(thermo, case, dtype):
     inputs = random_inputs(3000, seed=5)
-    got, want = _run_case(thermo, case, inputs, dtype)
-    for g, w in zip(got, want):
-        compare(case, g, w, dtype)
+    got, want, conds = _run_case(thermo, case, inputs, dtype)
+    for g, w, c in zip(got, want, conds):
+        compare(case, g, w, dtype, cond=c)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
@@ -49,9 +50,9 @@ def test_functors_match_oracle_random(thermo, case, dtype):
 def test_functors_match_oracle_edge(thermo, case, dtype):
     with np.errstate(all="ignore"):
         inputs = edge_inputs(n=600, seed=21)
-        got, want = _run_case(thermo, case, inputs, dtype)
-    for g, w in zip(got, want):
-        compare(case, g, w, dtype, edge=True)
+        got, want, conds = _run_case(thermo, case, inputs, dtype)
+    for g, w, c in zip(got, want, conds):
+        compare(case, g, w, dtype, edge=True, cond=c)
 
 
 @pytest.mark.parametrize("kat", KATS, ids=[f"{i}-{k[0]}" for i, k in enumerate(KATS)])
