@@ -7,7 +7,6 @@
 
 namespace ek {
 
-std::atomic<int> g_threads{256};
 std::atomic<int> g_ctas_per_sm{16};
 std::atomic<uint64_t> g_launches{0};
 
@@ -44,10 +43,7 @@ extern "C" EK_EXPORT const char* ek_thermo_last_error(void) { return t_err; }
 extern "C" EK_EXPORT uint64_t ek_thermo_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" EK_EXPORT int ek_thermo_set_launch_config(int threads, int ctas_per_sm) {
-    if (threads != 0) {
-        if (threads < 32 || threads > EK_MAX_THREADS || threads % 32) return set_error(EK_ERR_ARG, "threads=%d must be a multiple of 32 in [32, %d]", threads, EK_MAX_THREADS);
-        g_threads.store(threads);
-    }
+    if (threads != 0 && threads != kThreads) return set_error(EK_ERR_ARG, "threads=%d: the CTA size is fixed at build time (%d)", threads, kThreads);
     if (ctas_per_sm != 0) {
         if (ctas_per_sm < 1 || ctas_per_sm > 4096) return set_error(EK_ERR_ARG, "ctas_per_sm=%d out of range", ctas_per_sm);
         g_ctas_per_sm.store(ctas_per_sm);
@@ -69,6 +65,10 @@ extern "C" EK_EXPORT int ek_thermo_shard_range(int64_t n, int world, int rank, i
     *end = e;
     return EK_OK;
 }
+
+// defined in ek_ops_fused.cu (so the suite kernels are instantiated in one translation unit only)
+template <typename T> int ek_suite_launch_tqp(const ek_operand* ins, void* const* outs, uint32_t mask, int64_t n, void* stream);
+template <typename T> int ek_suite_launch_ttdp(const ek_operand* ins, void* const* outs, uint32_t mask, int64_t n, void* stream);
 
 // ---- host-buffer pipeline ---------------------------------------------------------------------------
 namespace {
@@ -127,8 +127,7 @@ static int impl_host_suite(int kind, const void* h_a, const void* h_b, const voi
         void* douts[S_NSLOTS];
         int j = 0;
         for (int k = 0; k < S_NSLOTS; ++k) douts[k] = ((out_mask >> k) & 1u) ? (void*)(base + (int64_t)(3 + j++) * chunk) : nullptr;
-        int rc = kind == 0 ? launch<OpSuiteTQP, T>("host_suite", ins, douts, m, Params{}, st)
-                           : launch<OpSuiteTTdP, T>("host_suite", ins, douts, m, Params{}, st);
+        int rc = kind == 0 ? ek_suite_launch_tqp<T>(ins, douts, out_mask, m, st) : ek_suite_launch_ttdp<T>(ins, douts, out_mask, m, st);
         if (rc != EK_OK) return rc;
         for (int k = 0; k < S_NSLOTS; ++k)
             if (douts[k]) {

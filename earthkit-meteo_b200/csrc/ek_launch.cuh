@@ -14,7 +14,6 @@ namespace ek {
 // defined in ek_api.cu
 int set_error(int code, const char* fmt, ...);
 int sm_count_current_device();
-extern std::atomic<int> g_threads;
 extern std::atomic<int> g_ctas_per_sm;
 extern std::atomic<uint64_t> g_launches;
 
@@ -22,7 +21,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Launch Op over n points.  ins[k].ptr == NULL means broadcast scalar ins[k].value; outs[o] == NULL means
 // "output o not wanted" (P.out_mask must agree).
-template <class Op, typename T>
+template <class Op, class OpE, typename T>
 int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n, Params P, void* stream) {
     if (n < 0) return set_error(EK_ERR_ARG, "%s: n=%lld must be >= 0", what, (long long)n);
     InArgs<Op::NIN> in;
@@ -54,7 +53,7 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     P.out_mask = mask;
     if (n == 0) return EK_OK;
 
-    const int threads = g_threads.load(std::memory_order_relaxed);
+    constexpr int threads = kThreads;
     const int64_t tile = (int64_t)threads * Vec16<T>::N * EK_UNROLL;
     const int64_t ntiles = n / tile;
     const int64_t tail_blocks = ((n - ntiles * tile) + threads - 1) / threads;
@@ -65,7 +64,7 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
 
-    ew_kernel<Op, T, EK_UNROLL><<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
+    ew_kernel<Op, OpE, T, EK_UNROLL><<<(unsigned)blocks, threads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));

@@ -7,7 +7,7 @@ using namespace ek;
     template <typename T> static int impl_##NAME(ek_operand a, void* out, int64_t n, void* stream) { \
         ek_operand ins[1] = {a};                                                                     \
         void* outs[1] = {out};                                                                       \
-        return launch<OP, T>(#NAME, ins, outs, n, Params{}, stream);                                 \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, Params{}, stream);                                 \
     }                                                                                                \
     EK_API(NAME, (ek_operand a, void* out, int64_t n, void* stream), (a, out, n, stream))
 
@@ -15,7 +15,7 @@ using namespace ek;
     template <typename T> static int impl_##NAME(ek_operand a, ek_operand b, void* out, int64_t n, void* stream) { \
         ek_operand ins[2] = {a, b};                                                                                \
         void* outs[1] = {out};                                                                                     \
-        return launch<OP, T>(#NAME, ins, outs, n, Params{}, stream);                                               \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, Params{}, stream);                                               \
     }                                                                                                              \
     EK_API(NAME, (ek_operand a, ek_operand b, void* out, int64_t n, void* stream), (a, b, out, n, stream))
 
@@ -23,7 +23,7 @@ using namespace ek;
     template <typename T> static int impl_##NAME(ek_operand a, ek_operand b, ek_operand c, void* out, int64_t n, void* stream) { \
         ek_operand ins[3] = {a, b, c};                                                                                           \
         void* outs[1] = {out};                                                                                                   \
-        return launch<OP, T>(#NAME, ins, outs, n, Params{}, stream);                                                             \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, Params{}, stream);                                                             \
     }                                                                                                                            \
     EK_API(NAME, (ek_operand a, ek_operand b, ek_operand c, void* out, int64_t n, void* stream), (a, b, c, out, n, stream))
 
@@ -57,7 +57,7 @@ EK_SIMPLE1(specific_gas_constant, OpGasConstant)
         void* outs[1] = {out};                                                                                                 \
         Params P;                                                                                                              \
         P.eps = eps;                                                                                                           \
-        return launch<OP, T>(#NAME, ins, outs, n, P, stream);                                                                  \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, P, stream);                                                                  \
     }                                                                                                                          \
     EK_API(NAME, (ek_operand a, ek_operand b, double eps, void* out, int64_t n, void* stream), (a, b, eps, out, n, stream))
 
@@ -72,7 +72,7 @@ EK_EPS2(mixing_ratio_from_vapour_pressure, OpWFromE)
         void* outs[1] = {out};                                                                                  \
         Params P;                                                                                               \
         P.opt0 = phase;                                                                                         \
-        return launch<OP, T>(#NAME, ins, outs, n, P, stream);                                                   \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, P, stream);                                                   \
     }                                                                                                           \
     EK_API(NAME, (ek_operand a, int phase, void* out, int64_t n, void* stream), (a, phase, out, n, stream))
 
@@ -83,7 +83,7 @@ EK_EPS2(mixing_ratio_from_vapour_pressure, OpWFromE)
         void* outs[1] = {out};                                                                                                \
         Params P;                                                                                                             \
         P.opt0 = phase;                                                                                                       \
-        return launch<OP, T>(#NAME, ins, outs, n, P, stream);                                                                 \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, P, stream);                                                                 \
     }                                                                                                                         \
     EK_API(NAME, (ek_operand a, ek_operand b, int phase, void* out, int64_t n, void* stream), (a, b, phase, out, n, stream))
 
@@ -105,7 +105,7 @@ EK_PHASE2(saturation_specific_humidity, OpQs)
         P.opt0 = phase;                                                                                                         \
         P.opt1 = (has_es ? 1 : 0) | (has_des ? 2 : 0);                                                                          \
         P.eps = eps;                                                                                                            \
-        return launch<OP, T>(#NAME, ins, outs, n, P, stream);                                                                   \
+        return launch<EK_OPS(OP), T>(#NAME, ins, outs, n, P, stream);                                                                   \
     }                                                                                                                           \
     EK_API(NAME,                                                                                                                \
            (ek_operand t, ek_operand p, ek_operand es, ek_operand des, int has_es, int has_des, int phase, double eps, void* out, \
@@ -122,7 +122,7 @@ template <typename T> static int impl_lcl_temperature(ek_operand t, ek_operand t
     void* outs[1] = {out};
     Params P;
     P.opt0 = method;
-    return launch<OpLclT, T>("lcl_temperature", ins, outs, n, P, stream);
+    return launch<EK_OPS(OpLclT), T>("lcl_temperature", ins, outs, n, P, stream);
 }
 EK_API(lcl_temperature, (ek_operand t, ek_operand td, int method, void* out, int64_t n, void* stream), (t, td, method, out, n, stream))
 
@@ -134,7 +134,7 @@ static int impl_lcl(ek_operand t, ek_operand td, ek_operand p, int method, void*
     void* outs[2] = {t_lcl, p_lcl};
     Params P;
     P.opt0 = method;
-    return launch<OpLcl, T>("lcl", ins, outs, n, P, stream);
+    return launch<EK_OPS(OpLcl), T>("lcl", ins, outs, n, P, stream);
 }
 EK_API(lcl, (ek_operand t, ek_operand td, ek_operand p, int method, void* t_lcl, void* p_lcl, int64_t n, void* stream),
        (t, td, p, method, t_lcl, p_lcl, n, stream))

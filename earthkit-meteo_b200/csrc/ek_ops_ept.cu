@@ -12,7 +12,7 @@ static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p
     Params P;
     P.opt0 = hum;
     P.opt1 = at_p0;
-    return launch<OpEptWb<M, TM>, T>("ept_wet_bulb", ins, outs, n, P, stream);
+    return launch<EK_OPS(OpEptWb<M, TM>), T>("ept_wet_bulb", ins, outs, n, P, stream);
 }
 
 template <typename T, int M>
@@ -74,9 +74,9 @@ template <typename T> static int impl_saturation_ept(ek_operand t, ek_operand p,
     ek_operand ins[2] = {t, p};
     void* outs[1] = {out};
     switch (m) {
-        case EK_EPT_IFS: return launch<OpSatEpt<EPT_IFS>, T>("saturation_ept", ins, outs, n, Params{}, stream);
-        case EK_EPT_BOLTON35: return launch<OpSatEpt<EPT_BOLTON35>, T>("saturation_ept", ins, outs, n, Params{}, stream);
-        case EK_EPT_BOLTON39: return launch<OpSatEpt<EPT_BOLTON39>, T>("saturation_ept", ins, outs, n, Params{}, stream);
+        case EK_EPT_IFS: return launch<EK_OPS(OpSatEpt<EPT_IFS>), T>("saturation_ept", ins, outs, n, Params{}, stream);
+        case EK_EPT_BOLTON35: return launch<EK_OPS(OpSatEpt<EPT_BOLTON35>), T>("saturation_ept", ins, outs, n, Params{}, stream);
+        case EK_EPT_BOLTON39: return launch<EK_OPS(OpSatEpt<EPT_BOLTON39>), T>("saturation_ept", ins, outs, n, Params{}, stream);
     }
     return set_error(EK_ERR_ENUM, "saturation_ept: invalid ept method id %d", m);
 }
@@ -84,8 +84,8 @@ EK_API(saturation_ept, (ek_operand t, ek_operand p, int m, void* out, int64_t n,
 
 // ---- temperature on a moist adiabat (T:1472-1509) ---------------------------------------------------
 template <typename T, int M> static int t_on_ma_m(int tm, const ek_operand* ins, void* const* outs, int64_t n, void* stream) {
-    if (tm == EK_TM_BISECT) return launch<OpTOnMa<M, TM_BISECT>, T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
-    if (tm == EK_TM_NEWTON) return launch<OpTOnMa<M, TM_NEWTON>, T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
+    if (tm == EK_TM_BISECT) return launch<EK_OPS(OpTOnMa<M, TM_BISECT>), T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
+    if (tm == EK_TM_NEWTON) return launch<EK_OPS(OpTOnMa<M, TM_NEWTON>), T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
     return set_error(EK_ERR_ENUM, "temperature_on_moist_adiabat: invalid t_method id %d", tm);
 }
 template <typename T>

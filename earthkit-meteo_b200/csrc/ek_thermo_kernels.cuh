@@ -13,13 +13,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "ek_thermo_ops.cuh"
+#include "ek_thermo_math.cuh"
 
 #ifndef EK_UNROLL
 #define EK_UNROLL 2
 #endif
 #ifndef EK_MAX_THREADS
 #define EK_MAX_THREADS 256
+#endif
+#ifndef EK_MIN_CTAS
+#define EK_MIN_CTAS 4  // <= 64 registers per thread: 4 CTAs = 32 warps per SM hide the fp64 dependency chains
 #endif
 
 namespace ek {
@@ -60,31 +63,72 @@ template <> struct Vec16<float> {
     }
 };
 
-template <class Op, typename T, int UNROLL>
-__global__ void __launch_bounds__(EK_MAX_THREADS)
-    ew_kernel(const InArgs<Op::NIN> in, const OutArgs<Op::NOUT> out, const int64_t n, const Params P, const int vec_ok) {
+// dynamic shared memory a launch must provide (the lean fp64 log/exp tables)
+#if EK_LEAN_MATH
+constexpr unsigned kSmemBytes = 2 * 8 * 128 + 8 * 64;  // lean::Tables (checked against sizeof in the kernel)
+#else
+constexpr unsigned kSmemBytes = 0;
+#endif
+
+constexpr int kThreads = EK_MAX_THREADS;  // CTA size is a compile-time constant: tile offsets become immediates
+
+// Cold path of a lean build: recompute one point with the exact functor (libdevice math, IEEE division).
+// Out of line on purpose: its registers and code stay out of the hot loop.
+template <class OpE, typename T> __device__ __noinline__ void exact_point(const T* a, T* r, const Params P) {
+    OpE::template apply<T>(a, r, P);
+}
+
+// True when a result of the fast functor may come from outside the lean primitives' domain (they answer NaN
+// there): the high word of a double NaN is >= 0x7ff80000 once the sign is cleared.
+template <int NOUT> __device__ __forceinline__ bool any_nan(const double* r) {
+    int m = 0;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) m = max(m, __double2hiint(r[o]) & 0x7fffffff);
+    return m >= 0x7ff80000;
+}
+template <int NOUT> __device__ __forceinline__ bool any_nan(const float*) { return false; }  // float32 lean math is self-contained
+
+// One grid point: fast functor, then (lean build, float64 only) the exact functor if the result has a NaN in it.
+template <class Op, class OpE, typename T> __device__ __forceinline__ void point(const T* a, T* r, const Params& P) {
+#pragma unroll
+    for (int o = 0; o < Op::NOUT; ++o) r[o] = T(0);
+    Op::template apply<T>(a, r, P);
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8 && __builtin_expect(any_nan<Op::NOUT>(r), 0)) {
+        T a2[Op::NIN], r2[Op::NOUT];
+#pragma unroll
+        for (int k = 0; k < Op::NIN; ++k) a2[k] = a[k];
+#pragma unroll
+        for (int o = 0; o < Op::NOUT; ++o) r2[o] = T(0);
+        exact_point<OpE, T>(a2, r2, P);
+#pragma unroll
+        for (int o = 0; o < Op::NOUT; ++o) r[o] = r2[o];
+    }
+#endif
+}
+
+template <class Op, class OpE, typename T, int UNROLL, bool VECOK>
+__device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P) {
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;
     constexpr int VEC = Vec16<T>::N;
-    const int64_t vec_stride = (int64_t)blockDim.x * VEC;  // elements between a thread's successive vectors
-    const int64_t tile_elems = vec_stride * UNROLL;
-    const int64_t ntiles = n / tile_elems;
-
+    constexpr int VSTRIDE = kThreads * VEC;  // elements between a thread's successive vectors
+    constexpr int TILE = VSTRIDE * UNROLL;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * tile_elems + (int64_t)threadIdx.x * VEC;
+        const int64_t base = tile * TILE + (int64_t)threadIdx.x * VEC;
         T x[NIN][UNROLL][VEC];
 #pragma unroll
         for (int k = 0; k < NIN; ++k) {
             if (in.p[k] != nullptr) {
                 const T* src = static_cast<const T*>(in.p[k]) + base;
-                if (vec_ok) {
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) Vec16<T>::load(src + u * vec_stride, x[k][u]);
-                } else {
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (VECOK) {
+                        Vec16<T>::load(src + u * VSTRIDE, x[k][u]);
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) x[k][u][v] = __ldcs(src + u * vec_stride + v);
+                        for (int v = 0; v < VEC; ++v) x[k][u][v] = __ldcs(src + u * VSTRIDE + v);
+                    }
                 }
             } else {
                 const T s = static_cast<T>(in.s[k]);
@@ -102,17 +146,16 @@ __global__ void __launch_bounds__(EK_MAX_THREADS)
                 T a[NIN], r[NOUT];
 #pragma unroll
                 for (int k = 0; k < NIN; ++k) a[k] = x[k][u][v];
-#pragma unroll
-                for (int o = 0; o < NOUT; ++o) r[o] = T(0);
-                Op::template apply<T>(a, r, P);
+                point<Op, OpE, T>(a, r, P);
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o) y[o][v] = r[o];
             }
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) {
-                if (out.p[o] != nullptr) {
-                    T* dst = static_cast<T*>(out.p[o]) + base + u * vec_stride;
-                    if (vec_ok) {
+                const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
+                if (w) {
+                    T* dst = static_cast<T*>(out.p[o]) + base + u * VSTRIDE;
+                    if (VECOK) {
                         Vec16<T>::store(dst, y[o]);
                     } else {
 #pragma unroll
@@ -122,19 +165,35 @@ __global__ void __launch_bounds__(EK_MAX_THREADS)
             }
         }
     }
+}
+
+template <class Op, class OpE, typename T, int UNROLL>
+__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS)
+    ew_kernel(const InArgs<Op::NIN> in, const OutArgs<Op::NOUT> out, const int64_t n, const Params P, const int vec_ok) {
+    constexpr int NIN = Op::NIN;
+    constexpr int NOUT = Op::NOUT;
+    constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
+#if EK_LEAN_DEVICE
+    static_assert(sizeof(lean::Tables) == kSmemBytes, "kSmemBytes must match lean::Tables");
+    if (sizeof(T) == 8) lean::init_tables();
+#endif
+    const int64_t ntiles = n / TILE;
+    if (vec_ok)
+        tile_loop<Op, OpE, T, UNROLL, true>(in, out, ntiles, P);
+    else
+        tile_loop<Op, OpE, T, UNROLL, false>(in, out, ntiles, P);
 
     // tail: fewer than one tile of points, one point per thread, grid-stride
-    for (int64_t i = ntiles * tile_elems + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         T a[NIN], r[NOUT];
 #pragma unroll
         for (int k = 0; k < NIN; ++k) a[k] = (in.p[k] != nullptr) ? __ldcs(static_cast<const T*>(in.p[k]) + i) : static_cast<T>(in.s[k]);
+        point<Op, OpE, T>(a, r, P);
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) r[o] = T(0);
-        Op::template apply<T>(a, r, P);
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o)
-            if (out.p[o] != nullptr) __stcs(static_cast<T*>(out.p[o]) + i, r[o]);
+        for (int o = 0; o < NOUT; ++o) {
+            const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
+            if (w) __stcs(static_cast<T*>(out.p[o]) + i, r[o]);
+        }
     }
 }
 

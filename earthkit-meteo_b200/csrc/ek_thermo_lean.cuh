@@ -1,0 +1,127 @@
+// ek_thermo_lean.cuh -- device-only math primitives sized for the instruction-issue budget of sm_100a.
+//
+// Why: with libdevice exp/log/pow and IEEE division the fused fp64 suite issues ~900 SASS instructions per
+// grid point -- two thirds of them UMOV/IMAD.MOV pairs that materialise 64-bit polynomial coefficients as
+// immediates -- and runs at 35 % of the HBM roofline, bound by instruction issue (profiles/r01_*).  These
+// replacements keep every constant in constant memory / uniform registers (one DFMA per Horner step, no
+// moves), use small shared-memory tables to shorten the polynomials, and drop work the path does not
+// need (correct rounding of the quotient, denormal results):
+//
+//   rcp_/div_  MUFU.RCP64H seed (2^-19.9, measured: tools/probe_mufu.cu) + one cubic Newton step: <= 2 ulp
+//   log_       128-entry {1/c, ln c} table, r = z/c - 1 (|r| < 2^-8), degree-6 log1p polynomial: ~1 ulp (abs 2e-16)
+//   exp_       64-entry 2^(j/64) table, degree-5 polynomial on |r| <= ln2/128: ~1 ulp
+//   pow_       exp_(y * log_(x)): relative error ~ |y ln x| * 2e-16
+//
+// The fp64 primitives are branch-free.  Outside their fast domain (x <= 0, denormal, inf, NaN for log_; |x| >= 708
+// or NaN for exp_; b = 0, denormal, inf, NaN for rcp_) they answer NaN; the kernel recomputes any point whose
+// result contains a NaN with the exact functor (cold path), so special values behave exactly as in the exact
+// build.  float32 uses hardware-approximate division and libdevice expf/logf, which are already short and
+// handle special values themselves.
+//
+// The tables live in shared memory (filled once per CTA by lean::init_tables from ek_thermo_kernels.cuh):
+// per-lane indexed reads from constant memory would serialise.
+#pragma once
+#include "ek_thermo_lean_tables.inc"
+
+namespace ek {
+namespace lean {
+
+struct Tables {
+    double2 log_tab[EK_LOG_TAB_N];  // {invc, logc}
+    double exp_tab[EK_EXP_TAB_N];   // 2^(j/64)
+};
+
+// polynomial coefficients: constant bank -> uniform registers, never immediates
+__constant__ double kLog[5] = {-0.5, 0x1.5555555555555p-2 /*1/3*/, -0.25, 0x1.999999999999ap-3 /*1/5*/, -0x1.5555555555555p-3 /*-1/6*/};
+__constant__ double kExp[4] = {0.5, 0x1.5555555555555p-3 /*1/6*/, 0x1.5555555555555p-5 /*1/24*/, 0x1.1111111111111p-7 /*1/120*/};
+__constant__ double kRed[8] = {EK_INVLN2_N, EK_LN2N_HI, EK_LN2N_LO, EK_LN2_HI, EK_LN2_LO, 0x1.8p52 /*magic*/, EK_LOG_P0, EK_LOG_T0DJ};
+
+__device__ __forceinline__ Tables* tables() {
+    extern __shared__ __align__(16) unsigned char ek_smem_raw[];
+    return reinterpret_cast<Tables*>(ek_smem_raw);
+}
+// Table reads go through explicit shared-state-space loads on a 32-bit address: with generic pointers the
+// compiler re-derives the shared window base (S2UR CgaCtaId + ULEA) at every access.
+__device__ __forceinline__ uint32_t tab_base() { return static_cast<uint32_t>(__cvta_generic_to_shared(tables())); }
+__device__ __forceinline__ double2 lds_log(int i) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(tab_base() + 16u * (uint32_t)i));
+    return v;
+}
+__device__ __forceinline__ double lds_exp(int j) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tab_base() + (uint32_t)(16 * EK_LOG_TAB_N) + 8u * (uint32_t)j));
+    return v;
+}
+
+__device__ __forceinline__ void init_tables() {
+    Tables* t = tables();
+    for (int i = threadIdx.x; i < EK_LOG_TAB_N; i += blockDim.x) t->log_tab[i] = make_double2(ek_log_tab_g[2 * i], ek_log_tab_g[2 * i + 1]);
+    for (int i = threadIdx.x; i < EK_EXP_TAB_N; i += blockDim.x) t->exp_tab[i] = ek_exp_tab_g[i];
+    __syncthreads();
+}
+
+// ---- float64 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_(double b) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+    const double e = fma(-b, r0, 1.0);
+    return fma(fma(e, e, e), r0, r0);  // b = 0, denormal, inf, NaN: e is NaN -> NaN (the point is recomputed exactly)
+}
+__device__ __forceinline__ double div_(double a, double b) { return a * rcp_(b); }
+
+__device__ __forceinline__ double log_(double x) {
+    const int hi = __double2hiint(x);
+    const bool bad = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;  // <= 0, denormal, inf, NaN: answer NaN
+    const int tmp = hi - 0x3fe60000;
+    const int i = (tmp >> 13) & (EK_LOG_TAB_N - 1);
+    const int k = tmp >> 20;
+    const double z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
+    const double2 tc = lds_log(i);
+    const double r = fma(z, tc.x, -1.0);
+    const double kd = (double)k;
+    const double r2 = r * r;
+    double p = fma(r, kLog[4], kLog[3]);
+    const double q = fma(r, kLog[2], kLog[1]);
+    p = fma(r2, p, q);
+    const double s = fma(r, p, kLog[0]);
+    const double t1 = fma(kd, kRed[3], tc.y);
+    const double t2 = fma(kd, kRed[4], r);
+    const double y = fma(r2, s, t2) + t1;
+    return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y), __double2loint(y));
+}
+
+__device__ __forceinline__ double exp_(double x) {
+    const bool bad = (unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x40862000u;  // |x| >= 708, inf, NaN: answer NaN
+    const double t = fma(x, kRed[0], kRed[5]);
+    const int ki = __double2loint(t);
+    const double kd = t - kRed[5];
+    double r = fma(kd, -kRed[1], x);
+    r = fma(kd, -kRed[2], r);
+    const double T = lds_exp(ki & (EK_EXP_TAB_N - 1));
+    const double r2 = r * r;
+    const double a = fma(r, kExp[1], kExp[0]);
+    const double b = fma(r, kExp[3], kExp[2]);
+    const double s = fma(r2, b, a);
+    const double p = fma(r2, s, r);
+    const double y = fma(T, p, T);
+    return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
+}
+
+__device__ __forceinline__ double pow_(double x, double y) { return exp_(y * log_(x)); }
+// pow(p0/x, y), pow(x/p0, y), pow(273.16/x, y): the logarithm of the constant is tabulated, no division
+__device__ __forceinline__ double pow_p0_over_(double x, double y) { return exp_(y * (kRed[6] - log_(x))); }
+__device__ __forceinline__ double pow_over_p0_(double x, double y) { return exp_(y * (log_(x) - kRed[6])); }
+__device__ __forceinline__ double pow_t0_over_(double x, double y) { return exp_(y * (kRed[7] - log_(x))); }
+
+// ---- float32 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float log_(float x) { return ::logf(x); }
+__device__ __forceinline__ float exp_(float x) { return ::expf(x); }
+__device__ __forceinline__ float pow_(float x, float y) { return ::expf(y * ::logf(x)); }
+__device__ __forceinline__ float pow_p0_over_(float x, float y) { return ::expf(y * ((float)EK_LOG_P0 - ::logf(x))); }
+__device__ __forceinline__ float pow_over_p0_(float x, float y) { return ::expf(y * (::logf(x) - (float)EK_LOG_P0)); }
+__device__ __forceinline__ float pow_t0_over_(float x, float y) { return ::expf(y * ((float)EK_LOG_T0DJ - ::logf(x))); }
+
+}  // namespace lean
+}  // namespace ek

@@ -8,9 +8,10 @@
 #include <cstring>
 #include <string>
 
-#include "../../earthkit-meteo_b200/csrc/ek_thermo_ops.cuh"
+#include "../../earthkit-meteo_b200/csrc/ek_thermo_math.cuh"
 
 using namespace ek;
+using namespace ek::exactm;
 
 template <class Op, typename T>
 static void run(const void* const* ins, const double* scalars, void* const* outs, int64_t n, const Params& P) {

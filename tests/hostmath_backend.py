@@ -20,7 +20,7 @@ SRC = os.path.join(HERE, "_hostmath", "hostmath.cpp")
 
 def build(force=False):
     hdr_dir = os.path.join(os.path.dirname(HERE), "earthkit-meteo_b200", "csrc")
-    deps = [SRC] + [os.path.join(hdr_dir, f) for f in ("ek_thermo_ops.cuh", "ek_thermo_math.cuh")]
+    deps = [SRC] + [os.path.join(hdr_dir, f) for f in ("ek_thermo_ops.inc", "ek_thermo_formulas.inc", "ek_thermo_math.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO])
     return SO

@@ -32,7 +32,7 @@ def _run_case(thermo, case, inputs, dtype):
     want = getattr(oracle, case.fn)(*args_np, **case.kwargs)
     if not isinstance(res, tuple):
         res, want = (res,), (want,)
-    conds = [None if case.iterative else conditioning(case, args_np, k) for k in range(len(res))]
+    conds = [None if case.iterative == "bisect" else conditioning(case, args_np, k) for k in range(len(res))]
     return [r.numpy() for r in res], want, conds
 
 
