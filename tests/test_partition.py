@@ -1,0 +1,91 @@
+"""CPU tests of the boundary itself: exported symbols, the field partitioner, and a world-size-2 gloo run."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ek_thermo.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = []
+    for m in re.finditer(r"EK_THERMO_FN\(\s*(\w+)\s*,", hdr):
+        if m.group(1) != "name":
+            names += [f"ek_thermo_{m.group(1)}_f64", f"ek_thermo_{m.group(1)}_f32"]
+    names += re.findall(r"^\s*(?:int|uint64_t|const char\*)\s+(ek_thermo_\w+)\s*\(", hdr, flags=re.M)
+    return sorted(set(names))
+
+
+@pytest.mark.parametrize("lib", ["libek_thermo.so", "libek_thermo_exact.so"])
+def test_library_loads_and_exports_every_declared_symbol(lib):
+    path = os.path.join(ROOT, "earthkit-meteo_b200", "ek_thermo", lib)
+    assert os.path.exists(path), "run __graft_entry__.build() first"
+    so = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 2 * 43 + 5
+    missing = [n for n in names if not hasattr(so, n)]
+    assert not missing, missing
+    so.ek_thermo_version.restype = ctypes.c_int
+    assert so.ek_thermo_version() == 100
+
+
+def test_python_binding_covers_the_reference_api():
+    import thermo_oracle as oracle
+    from ek_thermo import thermo
+
+    assert sorted(thermo.__all__) == sorted(oracle.PUBLIC_NAMES) and len(thermo.__all__) == 39
+    for name in oracle.PUBLIC_NAMES:
+        assert callable(getattr(thermo, name)) and callable(getattr(thermo.array, name))
+
+
+def test_argument_errors_without_a_gpu():
+    """Error paths that never reach a kernel launch."""
+    import torch
+
+    from ek_thermo import _backend, thermo
+
+    t = torch.ones(4, dtype=torch.float64)
+    with pytest.raises(TypeError):
+        thermo.potential_temperature(t, t)  # CPU tensor: no CPU path
+    with pytest.raises(TypeError):
+        thermo.potential_temperature(1.0, 2.0)  # no tensor at all
+    with pytest.raises(ValueError):
+        thermo.specific_humidity_from_vapour_pressure(t, t, eps=0.0)
+    with pytest.raises(KeyError):
+        thermo.ept_from_dewpoint(t, t, t, method="nope")
+    with pytest.raises(ValueError):
+        thermo.lcl(t, t, t, method="nope")
+    assert thermo.saturation_vapour_pressure(t, phase="nope") is None
+    with pytest.raises(ValueError):
+        _backend.set_launch_config(threads=100)
+    with pytest.raises(ValueError):
+        _backend.shard_range(10, 0, 0)
+
+
+@pytest.mark.parametrize("n,world,align", [(0, 1, 1), (10, 3, 1), (1000, 8, 16), (904156160, 8, 6599680), (11608481280, 8, 1661440),
+                                           (7, 8, 1), (1_000_003, 4, 2048)])
+def test_shard_ranges_partition_the_field(n, world, align):
+    from ek_thermo import partition
+
+    shards = partition.all_shards(n, world, align)
+    assert shards[0][0] == 0 and shards[-1][1] == n
+    for (b0, e0), (b1, e1) in zip(shards, shards[1:]):
+        assert e0 == b1 and b0 <= e0
+    for b, e in shards[:-1]:
+        assert b % align == 0 and e % align == 0
+    sizes = [e - b for b, e in shards[:-1]]
+    if sizes:
+        assert max(sizes) - min(sizes) <= align  # balanced to one slab
+
+
+def test_world_size_2_gloo():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
