@@ -16,7 +16,12 @@
 #include "ek_thermo_math.cuh"
 
 #ifndef EK_UNROLL
-#define EK_UNROLL 2
+#define EK_UNROLL 2  // 16-byte vectors per input per thread per tile
+#endif
+#ifndef EK_PIPELINE
+#define EK_PIPELINE 0  // 1: prefetch the next tile into a second register set before computing the current one.
+                       // Measured on B200 (profiles/r01_kbench_pipeline_unroll_variants.log): no gain over 0 -- 32 resident
+                       // warps/SM with 2 front-loaded vectors per input already cover the HBM latency -- so it stays off.
 #endif
 #ifndef EK_MAX_THREADS
 #define EK_MAX_THREADS 256
@@ -107,64 +112,105 @@ template <class Op, class OpE, typename T> __device__ __forceinline__ void point
 #endif
 }
 
+// The inputs of one tile, per thread: UNROLL 16-byte vectors of every input array, in registers.
+template <class Op, typename T, int UNROLL> struct TileRegs {
+    T x[Op::NIN][UNROLL][Vec16<T>::N];
+};
+
+template <class Op, typename T, int UNROLL, bool VECOK>
+__device__ __forceinline__ void load_tile(TileRegs<Op, T, UNROLL>& r, const InArgs<Op::NIN>& in, const int64_t base) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int VSTRIDE = kThreads * VEC;  // elements between a thread's successive vectors
+#pragma unroll
+    for (int k = 0; k < Op::NIN; ++k) {
+        if (in.p[k] != nullptr) {
+            const T* src = static_cast<const T*>(in.p[k]) + base;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (VECOK) {
+                    Vec16<T>::load(src + u * VSTRIDE, r.x[k][u]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r.x[k][u][v] = __ldcs(src + u * VSTRIDE + v);
+                }
+            }
+        } else {
+            const T s = static_cast<T>(in.s[k]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) r.x[k][u][v] = s;
+        }
+    }
+}
+
 template <class Op, class OpE, typename T, int UNROLL, bool VECOK>
-__device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P) {
+__device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>& r, const OutArgs<Op::NOUT>& out, const int64_t base,
+                                                   const Params& P) {
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;
     constexpr int VEC = Vec16<T>::N;
-    constexpr int VSTRIDE = kThreads * VEC;  // elements between a thread's successive vectors
-    constexpr int TILE = VSTRIDE * UNROLL;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * TILE + (int64_t)threadIdx.x * VEC;
-        T x[NIN][UNROLL][VEC];
+    constexpr int VSTRIDE = kThreads * VEC;
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) {
-            if (in.p[k] != nullptr) {
-                const T* src = static_cast<const T*>(in.p[k]) + base;
+    for (int u = 0; u < UNROLL; ++u) {
+        T y[NOUT][VEC];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    if (VECOK) {
-                        Vec16<T>::load(src + u * VSTRIDE, x[k][u]);
-                    } else {
+        for (int v = 0; v < VEC; ++v) {
+            T a[NIN], res[NOUT];
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) x[k][u][v] = __ldcs(src + u * VSTRIDE + v);
-                    }
-                }
-            } else {
-                const T s = static_cast<T>(in.s[k]);
+            for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
+            point<Op, OpE, T>(a, res, P);
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) x[k][u][v] = s;
-            }
+            for (int o = 0; o < NOUT; ++o) y[o][v] = res[o];
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            T y[NOUT][VEC];
+        for (int o = 0; o < NOUT; ++o) {
+            const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
+            if (w) {
+                T* dst = static_cast<T*>(out.p[o]) + base + u * VSTRIDE;
+                if (VECOK) {
+                    Vec16<T>::store(dst, y[o]);
+                } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                T a[NIN], r[NOUT];
-#pragma unroll
-                for (int k = 0; k < NIN; ++k) a[k] = x[k][u][v];
-                point<Op, OpE, T>(a, r, P);
-#pragma unroll
-                for (int o = 0; o < NOUT; ++o) y[o][v] = r[o];
-            }
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) {
-                const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
-                if (w) {
-                    T* dst = static_cast<T*>(out.p[o]) + base + u * VSTRIDE;
-                    if (VECOK) {
-                        Vec16<T>::store(dst, y[o]);
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) __stcs(dst + v, y[o][v]);
-                    }
+                    for (int v = 0; v < VEC; ++v) __stcs(dst + v, y[o][v]);
                 }
             }
         }
     }
+}
+
+// Tiles are handed to CTAs round-robin.  The loop is software-pipelined in registers: the loads of a CTA's NEXT
+// tile are issued before the math of the current one, so every warp keeps HBM requests in flight while it
+// computes (two register sets, A and B, alternate; no dynamic register indexing).
+template <class Op, class OpE, typename T, int UNROLL, bool VECOK>
+__device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P) {
+    constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
+    const int64_t G = gridDim.x;
+    const int64_t toff = (int64_t)threadIdx.x * Vec16<T>::N;
+    int64_t ta = blockIdx.x;
+    if (ta >= ntiles) return;
+#if EK_PIPELINE
+    TileRegs<Op, T, UNROLL> A, B;
+    load_tile<Op, T, UNROLL, VECOK>(A, in, ta * TILE + toff);
+    for (;;) {
+        const int64_t tb = ta + G;
+        const bool hb = tb < ntiles;
+        if (hb) load_tile<Op, T, UNROLL, VECOK>(B, in, tb * TILE + toff);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P);
+        if (!hb) break;
+        ta = tb + G;
+        const bool ha = ta < ntiles;
+        if (ha) load_tile<Op, T, UNROLL, VECOK>(A, in, ta * TILE + toff);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(B, out, tb * TILE + toff, P);
+        if (!ha) break;
+    }
+#else
+    for (; ta < ntiles; ta += G) {
+        TileRegs<Op, T, UNROLL> A;
+        load_tile<Op, T, UNROLL, VECOK>(A, in, ta * TILE + toff);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P);
+    }
+#endif
 }
 
 template <class Op, class OpE, typename T, int UNROLL>

@@ -114,6 +114,10 @@ __device__ __forceinline__ double pow_p0_over_(double x, double y) { return exp_
 __device__ __forceinline__ double pow_over_p0_(double x, double y) { return exp_(y * (log_(x) - kRed[6])); }
 __device__ __forceinline__ double pow_t0_over_(double x, double y) { return exp_(y * (kRed[7] - log_(x))); }
 
+// kappa * ln(p0 / x): the exponent of the Exner factor, for callers that fold it into a larger exponential
+__device__ __forceinline__ double kappa_log_p0_over(double x) { return ::ek::kCdev.kappa * (kRed[6] - log_(x)); }
+__device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek::kC.kappa * ((float)EK_LOG_P0 - ::logf(x)); }
+
 // ---- float32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ float log_(float x) { return ::logf(x); }

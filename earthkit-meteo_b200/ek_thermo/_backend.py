@@ -164,15 +164,21 @@ def _prepare(args):
     if not tensors:
         raise TypeError("ek_thermo: at least one argument must be a torch CUDA tensor")
     dev = _check_device(tensors)
-    dtype = tensors[0].dtype
-    for t in tensors[1:]:
-        dtype = torch.promote_types(dtype, t.dtype)
+    first = tensors[0]
+    dtype, shape = first.dtype, first.shape
+    uniform = True  # fast path: same dtype, same shape, contiguous -- the normal whole-field call
+    for t in tensors:
+        if t.dtype != dtype or t.shape != shape or not t.is_contiguous():
+            uniform = False
+            break
+    if not uniform:
+        for t in tensors[1:]:
+            dtype = torch.promote_types(dtype, t.dtype)
+        shape = torch.broadcast_shapes(*[t.shape for t in tensors])
     if dtype not in _SUFFIX:
+        uniform = False
         dtype = torch.float64 if not dtype.is_floating_point else (torch.float32 if dtype in (torch.float16, torch.bfloat16) else dtype)
-    shape = torch.broadcast_shapes(*[t.shape for t in tensors])
-    n = 1
-    for s in shape:
-        n *= int(s)
+    n = first.numel() if uniform else int(torch.Size(shape).numel())
     ops = []
     keep = []
     for it in items:
@@ -180,6 +186,8 @@ def _prepare(args):
             ops.append(ek_operand(None, 0.0))
         elif isinstance(it, float):
             ops.append(ek_operand(None, it))
+        elif uniform:
+            ops.append(ek_operand(it.data_ptr(), 0.0))
         else:
             t = it
             if t.numel() == 1 and n > 1:
@@ -199,9 +207,11 @@ def _prepare(args):
 def _call(symbol: str, dtype, device, c_args):
     """The one place where the C ABI is entered.  (Tests patch this to check the host logic on CPU.)"""
     fn = getattr(_lib, f"ek_thermo_{symbol}_{_SUFFIX[dtype]}")
+    if torch.cuda.current_device() == device.index:  # the usual case: no device switch needed
+        _check(fn(*c_args, c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        return
     with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        _check(fn(*c_args, c_void_p(stream)))
+        _check(fn(*c_args, c_void_p(torch.cuda.current_stream(device).cuda_stream)))
 
 
 def _empty(shape, dtype, device):

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""sweep.py -- field-size sweep (BASELINE.json configs[4]): grid-points/s and fraction of the HBM roofline vs N.
+
+    python tools/sweep.py [--dtype f64] [--max-bytes 1.2e11] > gpurun_out/sweep.jsonl
+
+Per-GPU numbers; with G GPUs the field is cut into G contiguous shards (ek_thermo.partition) that run
+independently, so the aggregate is G x the per-GPU figure at N/G points (no collective).
+Small N is launch-latency bound (Python call + ~5 us launch); the table shows where the roofline regime starts.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "earthkit-meteo_b200")]
+
+import torch  # noqa: E402
+
+from ek_thermo import fused, thermo  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--max-bytes", type=float, default=1.2e11)
+    a = ap.parse_args()
+    dt = torch.float64 if a.dtype == "f64" else torch.float32
+    esz = 8 if a.dtype == "f64" else 4
+    dev = "cuda:0"
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    sizes = [1_000_000, 3_000_000, 10_000_000, 30_000_000, 100_000_000, 300_000_000, 1_000_000_000, 3_000_000_000, 10_000_000_000]
+    g = torch.Generator(device=dev).manual_seed(0)
+    for n in sizes:
+        kernels = {"theta": 3, "rh_from_q": 4, "suite_tqp5": 8}
+        for name, narr in kernels.items():
+            if narr * esz * n > a.max_bytes:
+                print(json.dumps({"n": n, "kernel": name, "dtype": a.dtype, "skipped": "exceeds the per-GPU memory cap; shard it (ek_thermo.partition)"}), flush=True)
+                continue
+            t = torch.empty(n, device=dev, dtype=dt).uniform_(200.0, 320.0, generator=g)
+            p = torch.empty(n, device=dev, dtype=dt).uniform_(1.0e3, 1.05e5, generator=g)
+            q = torch.empty(n, device=dev, dtype=dt).uniform_(1.0e-6, 0.02, generator=g)
+            out = None
+            if name == "theta":
+                fn = lambda: thermo.potential_temperature(t, p)  # noqa: E731
+            elif name == "rh_from_q":
+                fn = lambda: thermo.relative_humidity_from_specific_humidity(t, q, p)  # noqa: E731
+            else:
+                out = {k: torch.empty_like(t) for k in fused.DEFAULT_TQP}
+                fn = lambda: fused.suite_tqp(t, q, p, out=out)  # noqa: E731
+            iters = max(5, min(2000, int(2e9 / n)))
+            # rotate over several buffers when the working set would sit in the 126 MB L2
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            gbs = narr * esz * n / ms / 1e6
+            print(json.dumps({"n": n, "kernel": name, "dtype": a.dtype, "ms": round(ms, 5), "gpts": round(n / ms / 1e6, 3), "gbs": round(gbs, 1),
+                              "frac_of_measured_hbm": round(gbs / peak, 4), "in_L2": narr * esz * n < 126e6, "iters": iters}), flush=True)
+            del t, p, q, out
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
