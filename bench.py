@@ -44,6 +44,8 @@ WORKLOADS = {
     "theta_rh_era5_f64": ("tqp", ("theta", "rh"), 1, 721 * 1440, "f64"),
     "ept_wbpt_o1280x137_f64": ("ept", ("ept", "wbpt"), N_LEVELS, O1280_POINTS, "f64"),
     "ept_wbpt_o1280x137_f32": ("ept", ("ept", "wbpt"), N_LEVELS, O1280_POINTS, "f32"),
+    # BASELINE.json configs[3]: one GPU's shard (of 8) of ENS 51 members x O640 x 137 levels, humidity conversions
+    "conv_ens_o640_shard_f64": ("tqp", ("rh", "td", "w"), 874, 4 * 640 * 649, "f64"),
 }
 DEFAULT_WORKLOAD = "suite_tqp_o1280x137_f64"
 
@@ -77,8 +79,11 @@ def make_inputs_device(kind, levels, npl, dtype, device, seed):
     ab = np.load(os.path.join(ROOT, "tests", "golden", "ifs_l137_ab.npz"))
     a_full = 0.5 * (ab["A"][:-1] + ab["A"][1:])
     b_full = 0.5 * (ab["B"][:-1] + ab["B"][1:])
-    if levels != a_full.size:  # short workloads use the lowest `levels` model levels
+    if levels < a_full.size:  # short workloads use the lowest `levels` model levels
         a_full, b_full = a_full[-levels:], b_full[-levels:]
+    elif levels > a_full.size:  # member x level slabs of an ensemble: the 137 levels repeat
+        sel = np.arange(levels) % a_full.size
+        a_full, b_full = a_full[sel], b_full[sel]
     a_l = torch.tensor(a_full, dtype=torch.float64, device=device).reshape(levels, 1)
     b_l = torch.tensor(b_full, dtype=torch.float64, device=device).reshape(levels, 1)
     sp = torch.empty(1, npl, dtype=torch.float64, device=device).uniform_(5.0e4, 1.05e5, generator=g)

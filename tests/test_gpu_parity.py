@@ -265,7 +265,7 @@ def test_fused_ept_wet_bulb_equals_separate_calls(ek, ept_method, t_method):
 def test_full_size_o1280_x137_properties(ek):
     """At 904 156 160 points the oracle cannot run in full; check size-independent properties instead:
     (i) the fused outputs equal the single-function kernels to 1e-14 over the whole field,
-    (ii) a strided sample of 2e5 points equals the oracle, (iii) kelvin<->celsius and theta<->t round trips."""
+    (ii) a strided sample of 1e6 points equals the oracle, (iii) kelvin<->celsius and theta<->t round trips."""
     from ek_thermo import fused
 
     n = 6599680 * 137
@@ -277,7 +277,7 @@ def test_full_size_o1280_x137_properties(ek):
     p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e3, 1.05e5, generator=g)
     q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
     out = fused.suite_tqp(t, q, p)
-    idx = torch.arange(0, n, 4513, device=DEV)
+    idx = torch.arange(0, n, 887, device=DEV)  # ~1.02e6 sampled points through the numpy oracle
     ts, qs, ps = (x[idx].cpu().numpy() for x in (t, q, p))
     with np.errstate(all="ignore"):
         want = oracle.suite_tqp(ts, qs, ps)
@@ -303,6 +303,82 @@ def test_full_size_o1280_x137_properties(ek):
     c = ek.thermo.kelvin_to_celsius(t)
     k2 = ek.thermo.celsius_to_kelvin(c)
     assert float((k2 - t).abs().max()) < 1e-12
+
+
+def test_full_size_config3_ept_wbpt_properties(ek):
+    """BASELINE.json configs[2]: ept + wet-bulb potential temperature on O1280 x 137 levels (904 156 160 points),
+    float64 and float32.  Properties: a strided 5e5-point sample equals the oracle; theta_e >= theta (q >= 0);
+    theta_w <= theta_e; the fused kernel equals the two single-output entry points on a level slab."""
+    from ek_thermo import fused
+
+    n = 6599680 * 137
+    free, _ = torch.cuda.mem_get_info()
+    if free < 45e9:
+        pytest.skip("needs ~40 GB of free HBM")
+    g = torch.Generator(device=DEV).manual_seed(1)
+    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(2.0e4, 1.05e5, generator=g)
+    t = (288.15 * (p / 101325.0) ** 0.19).add_(torch.empty(n, device=DEV, dtype=torch.float64).uniform_(-10.0, 10.0, generator=g))
+    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-6, 4.0e-3, generator=g)
+    idx = torch.arange(0, n, 1801, device=DEV)
+    for dt, rtol in ((torch.float64, 1e-12), (torch.float32, 2e-5)):
+        tt, qq, pp = t.to(dt), q.to(dt), p.to(dt)
+        ept, wb = fused.ept_wet_bulb(tt, qq, pp, humidity="q", ept_method="ifs", t_method="direct", potential=True)
+        ts, qs, ps = (x[idx].cpu().numpy() for x in (tt, qq, pp))
+        with np.errstate(all="ignore"):
+            want_e = oracle.ept_from_specific_humidity(ts, qs, ps).astype(np.float64)
+            want_w = np.asarray(oracle.wet_bulb_potential_temperature_from_specific_humidity(ts, qs, ps)).astype(np.float64)
+        got_e, got_w = ept[idx].cpu().numpy().astype(np.float64), wb[idx].cpu().numpy().astype(np.float64)
+        assert np.mean(np.abs(got_e - want_e) > rtol * np.abs(want_e)) <= (0.0 if dt == torch.float64 else 0.01)
+        assert np.mean(np.abs(got_w - want_w) > 4 * rtol * np.abs(want_w)) <= (0.0 if dt == torch.float64 else 0.01)
+        theta = ek.thermo.potential_temperature(tt, pp)
+        assert bool((ept >= theta * (1 - 1e-6)).all()) and bool((wb <= ept).all())
+        del theta
+        sl = slice(0, 6599680)
+        e1 = ek.thermo.ept_from_specific_humidity(tt[sl], qq[sl], pp[sl])
+        w1 = ek.thermo.wet_bulb_potential_temperature_from_specific_humidity(tt[sl], qq[sl], pp[sl])
+        torch.testing.assert_close(ept[sl], e1, rtol=(1e-13 if dt == torch.float64 else 1e-6), atol=0)
+        torch.testing.assert_close(wb[sl], w1, rtol=(1e-12 if dt == torch.float64 else 1e-5), atol=0)
+        del ept, wb, tt, qq, pp, e1, w1
+
+
+def test_full_size_config4_ens_shard_conversions(ek):
+    """BASELINE.json configs[3]: one GPU's shard of ENS 51 x O640 x 137 (1 451 060 160 points), humidity / dewpoint
+    conversions.  Round trips through the inverse functions over the whole shard (size-independent properties),
+    a sampled comparison with the oracle, and the shard edges produced by the partitioner."""
+    from ek_thermo import fused, partition
+
+    n_total, slab = 51 * 137 * 1661440, 1661440
+    b, e = partition.shard_range(n_total, 8, 3, align=slab)
+    n = e - b
+    assert n in (873 * slab, 874 * slab)
+    free, _ = torch.cuda.mem_get_info()
+    if free < 75e9:
+        pytest.skip("needs ~70 GB of free HBM")
+    g = torch.Generator(device=DEV).manual_seed(2)
+    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(3.0e4, 1.05e5, generator=g)
+    t = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(235.0, 310.0, generator=g)
+    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-5, 2.0e-3, generator=g)
+    th = ek.thermo
+    td = th.dewpoint_from_specific_humidity(q, p)
+    q2 = th.specific_humidity_from_dewpoint(td, p)
+    assert float(((q2 - q).abs() / q).max()) < 1e-11  # q -> td -> q
+    del q2
+    r = th.relative_humidity_from_dewpoint(t, td)
+    td2 = th.dewpoint_from_relative_humidity(t, r)
+    assert float(((td2 - td).abs() / td).max()) < 1e-12  # td -> r -> td
+    del td2, r
+    w = th.mixing_ratio_from_specific_humidity(q)
+    q3 = th.specific_humidity_from_mixing_ratio(w)
+    assert float(((q3 - q).abs() / q).max()) < 1e-14
+    del q3
+    out = fused.suite_tqp(t, q, p, outputs=("rh", "td", "w"))
+    torch.testing.assert_close(out["td"], td, rtol=1e-14, atol=0)
+    torch.testing.assert_close(out["w"], w, rtol=1e-14, atol=0)
+    idx = torch.arange(0, n, 2903, device=DEV)
+    ts, qs, ps = (x[idx].cpu().numpy() for x in (t, q, p))
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(out["rh"][idx].cpu().numpy(), oracle.relative_humidity_from_specific_humidity(ts, qs, ps), rtol=1e-12)
+        np.testing.assert_allclose(td[idx].cpu().numpy(), oracle.dewpoint_from_specific_humidity(qs, ps), rtol=1e-12)
 
 
 # ---- host-buffer pipeline and partitioner -----------------------------------------------------------
