@@ -45,6 +45,8 @@ WORKLOADS = {
     "ept_wbpt_o1280x137_f64": ("ept", ("ept", "wbpt"), N_LEVELS, O1280_POINTS, "f64"),
     "ept_wbpt_o1280x137_f32": ("ept", ("ept", "wbpt"), N_LEVELS, O1280_POINTS, "f32"),
     # BASELINE.json configs[3]: one GPU's shard (of 8) of ENS 51 members x O640 x 137 levels, humidity conversions
+    # the same suite with the pressure computed in-kernel from sp and the L137 A/B (56 B/pt)
+    "suite_tq_hybrid_o1280x137_f64": ("hybrid", ("theta", "es", "rh", "td", "tv"), N_LEVELS, O1280_POINTS, "f64"),
     "conv_ens_o640_shard_f64": ("tqp", ("rh", "td", "w"), 874, 4 * 640 * 649, "f64"),
 }
 DEFAULT_WORKLOAD = "suite_tqp_o1280x137_f64"
@@ -89,8 +91,16 @@ def make_inputs_device(kind, levels, npl, dtype, device, seed):
     sp = torch.empty(1, npl, dtype=torch.float64, device=device).uniform_(5.0e4, 1.05e5, generator=g)
     p = torch.empty(levels, npl, dtype=torch.float64, device=device)
     t = torch.empty(levels, npl, dtype=torch.float64, device=device)
+    sp_keep = sp[0].clone() if kind == "hybrid" else None
+    if kind == "hybrid":  # exactly the reference's full-level pressure: ph0 + 0.5 * (ph1 - ph0)  (vertical.py:663,708)
+        a_h64 = torch.tensor(ab["A"], dtype=torch.float64, device=device)
+        b_h64 = torch.tensor(ab["B"], dtype=torch.float64, device=device)
     for k in range(levels):  # level by level to bound temporaries
-        p[k] = a_l[k] + b_l[k] * sp[0]
+        if kind == "hybrid":
+            ph0, ph1 = a_h64[k] + b_h64[k] * sp[0], a_h64[k + 1] + b_h64[k + 1] * sp[0]
+            p[k] = ph0 + 0.5 * (ph1 - ph0)
+        else:
+            p[k] = a_l[k] + b_l[k] * sp[0]
         noise = torch.empty(npl, dtype=torch.float64, device=device).uniform_(-15.0, 15.0, generator=g)
         t[k] = (288.15 * (p[k] / 101325.0) ** 0.19 + noise).clamp_(180.0, 320.0)
     del sp
@@ -103,6 +113,11 @@ def make_inputs_device(kind, levels, npl, dtype, device, seed):
             qs = thermo.saturation_specific_humidity(t[k], p[k])
             h[k] = torch.where(torch.isnan(qs), u, torch.minimum(u, 0.95 * qs.abs()))
     tdt = torch.float64 if dtype == "f64" else torch.float32
+    if kind == "hybrid":  # hand the kernel sp and the half-level coefficients instead of the pressure field
+        a_h = torch.tensor(ab["A"], dtype=tdt, device=device)
+        b_h = torch.tensor(ab["B"], dtype=tdt, device=device)
+        del p
+        return [t.reshape(-1).to(tdt), h.reshape(-1).to(tdt), (sp_keep.reshape(-1).to(tdt), a_h, b_h)]
     return [x.reshape(-1).to(tdt) for x in (t, h, p)]
 
 
@@ -127,6 +142,17 @@ def build_step(kind, outputs, arrays):
 
     t, h, p = arrays
     esz = t.element_size()
+    if kind == "hybrid":  # p is (sp, A, B): [npl] + 2 x (nlev + 1)
+        sp, a, b = p
+        nlev = a.numel() - 1
+        t2, h2 = t.reshape(nlev, -1), h.reshape(nlev, -1)
+        out = {name: torch.empty_like(t2) for name in outputs}
+
+        def step():
+            fused.suite_tq_hybrid(t2, h2, sp, a, b, outputs=outputs, out=out)
+
+        # per point: t, q read, outputs written; sp is read once per point COLUMN (8/nlev B per point)
+        return step, esz * (2 + len(outputs)) + esz / nlev, {k: v.reshape(-1) for k, v in out.items()}
     if kind in ("tqp", "ttdp"):
         out = {name: torch.empty_like(t) for name in outputs}
         fn = fused.suite_tqp if kind == "tqp" else fused.suite_ttdp
@@ -383,7 +409,7 @@ def run_ours(args, kind, outputs, levels, npl, dtype):
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = bytes_per_pt * n / (ms_step * 1e-3) / 1e9  # per GPU: one kernel per step
-        cpu = cpu_baseline_single_core(kind, outputs, min(npl, O1280_POINTS), dtype) if world == 1 and not args.no_cpu else None
+        cpu = cpu_baseline_single_core("tqp" if kind == "hybrid" else kind, outputs, min(npl, O1280_POINTS), dtype) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "grid-points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
@@ -392,7 +418,8 @@ def run_ours(args, kind, outputs, levels, npl, dtype):
                        "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (bytes_per_pt * n / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.workload), "peak_source": peak_src,
-                         "kernel": "ew_kernel<%s>" % ("OpEptWb" if kind == "ept" else ("OpSuiteTQP" if kind == "tqp" else "OpSuiteTTdP")),
+                         "kernel": {"ept": "ew_kernel<OpEptWb>", "tqp": "ew_kernel<OpSuiteTQPm>", "ttdp": "ew_kernel<OpSuiteTTdPm>",
+                                    "hybrid": "suite_hybrid_kernel<OpSuiteTQPm>"}[kind],
                          "algorithmic_bytes_per_launch": bytes_per_pt * n, "avg_launch_ms": ms_step},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
@@ -418,7 +445,7 @@ def main():
     if args.levels:
         levels = args.levels
     if args.impl == "reference":
-        run_reference(args, kind, outputs, levels, npl, dtype)
+        run_reference(args, "tqp" if kind == "hybrid" else kind, outputs, levels, npl, dtype)
     else:
         run_ours(args, kind, outputs, levels, npl, dtype)
 

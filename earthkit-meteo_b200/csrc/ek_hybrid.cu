@@ -1,0 +1,333 @@
+// ek_hybrid.cu -- hybrid (IFS model) level pressure, stand-alone and fused into the (t, q) thermo suite.
+//
+// `pressure_on_hybrid_levels` (reference vertical/array/vertical.py:505-737, "V") is the step
+// right before the thermo path on model levels: it expands surface pressure sp[point] and the A/B half-level
+// coefficients into the [level, point] pressure field the thermo kernels read.  Two kernels:
+//
+//   hybrid_pressure_kernel   any of {full, half, delta, alpha} for a list of levels: sp is read once per point
+//                            tile and every requested row is written from registers (write-bound streaming).
+//   suite_hybrid_kernel      the fused (t, q, p) suite with p computed in registers from sp and A/B: the
+//                            [level, point] pressure array is never materialised or read (64 -> 56 B/pt).
+//
+// Work item = (tile of 256 x VEC points, chunk of levels); items are handed to CTAs round-robin.  A/B are read
+// through the read-only path with a warp-uniform address (broadcast).  Same lean-math + exact-recompute scheme
+// as ek_thermo_kernels.cuh.
+#include "ek_launch.cuh"
+
+using namespace ek;
+
+// levels whose t/q loads are in flight per thread.  Measured on B200 (O1280 x 137, fp64): 2 -> 10.3-11.0 ms,
+// 3 -> 12.0 ms, 4 -> 13.9 ms (register pressure at the 64-register cap), so 2.
+#ifndef EK_HYB_LU
+#define EK_HYB_LU 2
+#endif
+
+namespace {
+
+template <typename T> __device__ __forceinline__ bool is_nan_bits(T v);
+template <> __device__ __forceinline__ bool is_nan_bits<double>(double v) { return (__double2hiint(v) & 0x7fffffff) >= 0x7ff80000; }
+template <> __device__ __forceinline__ bool is_nan_bits<float>(float) { return false; }
+
+template <typename T> __device__ __noinline__ void exact_delta_alpha(T ph0, T ph1, bool top, T at, T* d, T* a) {
+    exactm::hyb_delta_alpha<T>(ph0, ph1, top, at, *d, *a);
+}
+
+template <typename T> __device__ __forceinline__ void delta_alpha(T ph0, T ph1, bool top, T at, T& d, T& a) {
+#if EK_LEAN_DEVICE
+    fastm::hyb_delta_alpha<T>(ph0, ph1, top, at, d, a);
+    if (sizeof(T) == 8 && __builtin_expect(is_nan_bits(d) || is_nan_bits(a), 0)) {
+        T d2, a2;
+        exact_delta_alpha<T>(ph0, ph1, top, at, &d2, &a2);
+        d = d2;
+        a = a2;
+    }
+#else
+    exactm::hyb_delta_alpha<T>(ph0, ph1, top, at, d, a);
+#endif
+}
+
+// loads / stores of one thread's VEC consecutive points of a row; vector path when aligned and in range
+template <typename T, bool VECOK> __device__ __forceinline__ void ld_row(const T* row, int64_t i0, int64_t npl, T* v, bool streaming) {
+    constexpr int VEC = Vec16<T>::N;
+    if (VECOK && i0 + VEC <= npl) {
+        if (streaming) {
+            Vec16<T>::load(row + i0, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = __ldg(row + i0 + j);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = (i0 + j < npl) ? __ldg(row + i0 + j) : T(1);
+    }
+}
+template <typename T, bool VECOK> __device__ __forceinline__ void st_row(T* row, int64_t i0, int64_t npl, const T* v) {
+    constexpr int VEC = Vec16<T>::N;
+    if (VECOK && i0 + VEC <= npl) {
+        Vec16<T>::store(row + i0, v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            if (i0 + j < npl) __stcs(row + i0 + j, v[j]);
+    }
+}
+
+struct HybridArgs {
+    const void* sp;
+    const void* A;         // nhalf half-level coefficients (device)
+    const void* B;
+    const int* full_rows;  // full-level index k (0-based) of every full/delta/alpha output row
+    const int* half_rows;  // half-level index of every half output row
+    int n_full, n_half;
+    int top_k;     // the full level treated as the column top (first level of the computed band, V:645-647)
+    int top_toa;   // any(p_half[top] <= 0.1) over the field (V:678)
+    double alpha_top;
+    void *full, *half, *delta, *alpha;
+    int64_t npl;
+    int rows_per_item;
+};
+
+template <typename T, bool VECOK>
+__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) hybrid_pressure_kernel(const HybridArgs g) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int TILE = kThreads * VEC;
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8) lean::init_tables();
+#endif
+    const T* A = static_cast<const T*>(g.A);
+    const T* B = static_cast<const T*>(g.B);
+    const int64_t ptiles = (g.npl + TILE - 1) / TILE;
+    const int n_rows = g.n_full > g.n_half ? g.n_full : g.n_half;
+    const int chunks = (n_rows + g.rows_per_item - 1) / g.rows_per_item;
+    const int64_t items = ptiles * chunks;
+    const bool want_da = g.delta != nullptr || g.alpha != nullptr;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t pt = it / chunks;
+        const int r0 = (int)(it - pt * chunks) * g.rows_per_item;
+        const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
+        if (i0 >= g.npl) continue;
+        T sp[VEC];
+        ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+        for (int r = r0; r < r0 + g.rows_per_item; ++r) {
+            if (r < g.n_full && (g.full != nullptr || want_da)) {
+                const int k = g.full_rows[r];
+                const T a0 = __ldg(A + k), b0 = __ldg(B + k), a1 = __ldg(A + k + 1), b1 = __ldg(B + k + 1);
+                const bool top = g.top_toa && k == g.top_k;
+                T f[VEC], d[VEC], al[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const T ph0 = exactm::hyb_half(a0, b0, sp[j]), ph1 = exactm::hyb_half(a1, b1, sp[j]);
+                    f[j] = exactm::hyb_full(ph0, ph1);
+                    if (want_da) delta_alpha<T>(ph0, ph1, top, static_cast<T>(g.alpha_top), d[j], al[j]);
+                }
+                const int64_t off = (int64_t)r * g.npl;
+                if (g.full) st_row<T, VECOK>(static_cast<T*>(g.full) + off, i0, g.npl, f);
+                if (g.delta) st_row<T, VECOK>(static_cast<T*>(g.delta) + off, i0, g.npl, d);
+                if (g.alpha) st_row<T, VECOK>(static_cast<T*>(g.alpha) + off, i0, g.npl, al);
+            }
+            if (r < g.n_half && g.half != nullptr) {
+                const int h = g.half_rows[r];
+                const T a0 = __ldg(A + h), b0 = __ldg(B + h);
+                T ph[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) ph[j] = exactm::hyb_half(a0, b0, sp[j]);
+                st_row<T, VECOK>(static_cast<T*>(g.half) + (int64_t)r * g.npl, i0, g.npl, ph);
+            }
+        }
+    }
+}
+
+// any(A0 + B0 * sp <= thr) over the field (V:678): one flag for the whole launch
+template <typename T> __global__ void any_le_kernel(const T* sp, int64_t n, T a0, T b0, T thr, int* flag) {
+    int hit = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        hit |= (exactm::hyb_half(a0, b0, __ldg(sp + i)) <= thr) ? 1 : 0;
+    if (__syncthreads_or(hit) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+struct SuiteHybridArgs {
+    const void *t, *q, *sp, *A, *B;  // t, q: [nlev, npl]; sp: [npl]; A, B: nlev + 1 half-level coefficients
+    void* outs[S_NSLOTS];
+    void* p_out;  // optional: the full-level pressure itself
+    int nlev;
+    int64_t npl;
+    int rows_per_item;
+};
+
+template <class Op, class OpE, typename T, bool VECOK>
+__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) suite_hybrid_kernel(const SuiteHybridArgs g, const Params P) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int TILE = kThreads * VEC;
+    constexpr int LU = EK_HYB_LU;  // levels in flight per thread (their loads are issued before any math)
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8) lean::init_tables();
+#endif
+    const T* A = static_cast<const T*>(g.A);
+    const T* B = static_cast<const T*>(g.B);
+    const T* tq[2] = {static_cast<const T*>(g.t), static_cast<const T*>(g.q)};
+    const int64_t ptiles = (g.npl + TILE - 1) / TILE;
+    const int chunks = (g.nlev + g.rows_per_item - 1) / g.rows_per_item;
+    const int64_t items = ptiles * chunks;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t pt = it / chunks;
+        const int k0 = (int)(it - pt * chunks) * g.rows_per_item;
+        const int k1 = min(k0 + g.rows_per_item, g.nlev);
+        const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
+        if (i0 >= g.npl) continue;
+        T sp[VEC];
+        ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+        for (int k = k0; k < k1; k += LU) {
+            T x[LU][2][VEC];
+#pragma unroll
+            for (int u = 0; u < LU; ++u)
+                if (k + u < k1) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) ld_row<T, VECOK>(tq[c] + (int64_t)(k + u) * g.npl, i0, g.npl, x[u][c], true);
+                }
+#pragma unroll
+            for (int u = 0; u < LU; ++u) {
+                if (k + u >= k1) break;
+                const int kk = k + u;
+                const T a0 = __ldg(A + kk), b0 = __ldg(B + kk), a1 = __ldg(A + kk + 1), b1 = __ldg(B + kk + 1);
+                T y[S_NSLOTS][VEC], pf[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    pf[j] = exactm::hyb_full(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]));
+                    T a[3] = {x[u][0][j], x[u][1][j], pf[j]}, r[S_NSLOTS];
+                    point<Op, OpE, T>(a, r, P);
+#pragma unroll
+                    for (int o = 0; o < S_NSLOTS; ++o) y[o][j] = r[o];
+                }
+                const int64_t off = (int64_t)kk * g.npl;
+#pragma unroll
+                for (int o = 0; o < S_NSLOTS; ++o) {
+                    const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (g.outs[o] != nullptr);
+                    if (w) st_row<T, VECOK>(static_cast<T*>(g.outs[o]) + off, i0, g.npl, y[o]);
+                }
+                if (g.p_out) st_row<T, VECOK>(static_cast<T*>(g.p_out) + off, i0, g.npl, pf);
+            }
+        }
+    }
+}
+
+int grid_for(int64_t items) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return -1;
+    const int64_t cap = (int64_t)sms * g_ctas_per_sm.load(std::memory_order_relaxed);
+    return (int)(items < cap ? (items > 0 ? items : 1) : cap);
+}
+
+// levels per work item: enough items to balance the grid, at least 2 levels each
+int rows_per_item_for(int64_t ptiles, int n_rows) {
+    const int sms = sm_count_current_device();
+    const int64_t want_items = (int64_t)(sms > 0 ? sms : 148) * 64;
+    int64_t chunks = (want_items + ptiles - 1) / ptiles;
+    if (chunks < 1) chunks = 1;
+    int rpi = (int)((n_rows + chunks - 1) / chunks);
+    if (rpi < 2) rpi = 2;
+    if (rpi & 1) ++rpi;
+    return rpi;
+}
+
+bool ok16(const void* p) { return p == nullptr || aligned16(p); }
+
+}  // namespace
+
+template <typename T>
+static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows, int n_full,
+                                          const int* half_rows, int n_half, int top_k, int top_toa, double alpha_top, void* full, void* half,
+                                          void* delta, void* alpha, void* stream) {
+    const char* what = "pressure_on_hybrid_levels";
+    if (!A || !B || !sp || nhalf < 2 || npl < 0 || n_full < 0 || n_half < 0) return set_error(EK_ERR_ARG, "%s: bad arguments", what);
+    if (!full && !half && !delta && !alpha) return set_error(EK_ERR_ARG, "%s: no output buffer given", what);
+    if ((full || delta || alpha) && (n_full < 1 || !full_rows)) return set_error(EK_ERR_ARG, "%s: full/delta/alpha need full_rows", what);
+    if (half && (n_half < 1 || !half_rows)) return set_error(EK_ERR_ARG, "%s: half needs half_rows", what);
+    if (npl == 0) return EK_OK;
+    HybridArgs g{sp, A, B, full_rows, half_rows, (full || delta || alpha) ? n_full : 0, half ? n_half : 0, top_k, top_toa, alpha_top,
+                 full, half, delta, alpha, npl, 2};
+    constexpr int TILE = kThreads * Vec16<T>::N;
+    const int64_t ptiles = (npl + TILE - 1) / TILE;
+    const int n_rows = g.n_full > g.n_half ? g.n_full : g.n_half;
+    g.rows_per_item = rows_per_item_for(ptiles, n_rows);
+    const int64_t items = ptiles * ((n_rows + g.rows_per_item - 1) / g.rows_per_item);
+    const int blocks = grid_for(items);
+    if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
+    const bool vec = npl % Vec16<T>::N == 0 && ok16(sp) && ok16(full) && ok16(half) && ok16(delta) && ok16(alpha);
+    if (vec)
+        hybrid_pressure_kernel<T, true><<<blocks, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    else
+        hybrid_pressure_kernel<T, false><<<blocks, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    return EK_OK;
+}
+EK_API(pressure_on_hybrid_levels,
+       (const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows, int n_full, const int* half_rows, int n_half,
+        int top_k, int top_toa, double alpha_top, void* full, void* half, void* delta, void* alpha, void* stream),
+       (A, B, nhalf, sp, npl, full_rows, n_full, half_rows, n_half, top_k, top_toa, alpha_top, full, half, delta, alpha, stream))
+
+template <typename T>
+static int impl_hybrid_top_is_toa(const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream) {
+    if (!sp || !flag || npl < 0) return set_error(EK_ERR_ARG, "hybrid_top_is_toa: bad arguments");
+    if (npl == 0) return EK_OK;
+    const int blocks = grid_for((npl + 255) / 256);
+    if (blocks < 0) return set_error(EK_ERR_ARG, "hybrid_top_is_toa: no CUDA device is current");
+    any_le_kernel<T><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(sp), npl, (T)a_top, (T)b_top, (T)0.1, flag);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error((int)err, "hybrid_top_is_toa: kernel launch failed: %s", cudaGetErrorString(err));
+    return EK_OK;
+}
+EK_API(hybrid_top_is_toa, (const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream), (sp, npl, a_top, b_top, flag, stream))
+
+template <template <uint32_t> class OpM, template <uint32_t> class OpME, typename T>
+static int suite_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs,
+                        uint32_t out_mask, void* p_out, void* stream) {
+    const char* what = "suite_tq_hybrid";
+    if (!t || !q || !sp || !A || !B || nlev < 1 || npl < 0) return set_error(EK_ERR_ARG, "%s: bad arguments", what);
+    if (out_mask >= (1u << S_NSLOTS) || (out_mask == 0 && !p_out)) return set_error(EK_ERR_ARG, "%s: out_mask=0x%x selects no output", what, out_mask);
+    SuiteHybridArgs g{t, q, sp, A, B, {}, p_out, nlev, npl, 2};
+    bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(p_out);
+    for (int k = 0; k < S_NSLOTS; ++k) {
+        g.outs[k] = ((out_mask >> k) & 1u) ? (outs ? outs[k] : nullptr) : nullptr;
+        if (((out_mask >> k) & 1u) && !g.outs[k]) return set_error(EK_ERR_ARG, "%s: output %d requested but its buffer is NULL", what, k);
+        vec = vec && ok16(g.outs[k]);
+    }
+    if (npl == 0) return EK_OK;
+    constexpr int TILE = kThreads * Vec16<T>::N;
+    const int64_t ptiles = (npl + TILE - 1) / TILE;
+    g.rows_per_item = rows_per_item_for(ptiles, nlev);
+    const int64_t items = ptiles * ((nlev + g.rows_per_item - 1) / g.rows_per_item);
+    const int blocks = grid_for(items);
+    if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
+    Params P;
+    P.out_mask = out_mask;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define EK_LAUNCH_SH(M)                                                                          \
+    do {                                                                                         \
+        if (vec)                                                                                 \
+            suite_hybrid_kernel<OpM<M>, OpME<M>, T, true><<<blocks, kThreads, kSmemBytes, st>>>(g, P);  \
+        else                                                                                     \
+            suite_hybrid_kernel<OpM<M>, OpME<M>, T, false><<<blocks, kThreads, kSmemBytes, st>>>(g, P); \
+    } while (0)
+    if (out_mask == 0x1F)
+        EK_LAUNCH_SH(0x1F);
+    else
+        EK_LAUNCH_SH(0);
+#undef EK_LAUNCH_SH
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    return EK_OK;
+}
+
+template <typename T>
+static int impl_suite_tq_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,
+                                void* const* outs, uint32_t out_mask, void* p_out, void* stream) {
+    return suite_hybrid<EK_OPS(OpSuiteTQPm), T>(t, q, sp, A, B, nlev, npl, outs, out_mask, p_out, stream);
+}
+EK_API(suite_tq_hybrid,
+       (const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs, uint32_t out_mask,
+        void* p_out, void* stream),
+       (t, q, sp, A, B, nlev, npl, outs, out_mask, p_out, stream))

@@ -95,6 +95,18 @@ for _name in ("suite_tqp", "suite_ttdp"):
         _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
         _fn.argtypes = [ek_operand] * 3 + [ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p]
         _fn.restype = c_int
+_c_int_p = ctypes.POINTER(c_int)
+for _sfx in ("f64", "f32"):
+    _fn = getattr(_lib, f"ek_thermo_pressure_on_hybrid_levels_{_sfx}")
+    _fn.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double,
+                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    _fn.restype = c_int
+    _fn = getattr(_lib, f"ek_thermo_hybrid_top_is_toa_{_sfx}")
+    _fn.argtypes = [c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p]
+    _fn.restype = c_int
+    _fn = getattr(_lib, f"ek_thermo_suite_tq_hybrid_{_sfx}")
+    _fn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, ctypes.POINTER(c_void_p), c_uint32, c_void_p, c_void_p]
+    _fn.restype = c_int
 for _sfx in ("f64", "f32"):
     _fn = getattr(_lib, f"ek_thermo_host_suite_{_sfx}")
     _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p, c_size_t, c_int]
@@ -212,6 +224,11 @@ def _call(symbol: str, dtype, device, c_args):
         return
     with torch.cuda.device(device):
         _check(fn(*c_args, c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+
+
+def call_raw(symbol: str, dtype, device, *c_args):
+    """Entry points whose argument list does not follow the operands/options/outputs pattern (stream appended)."""
+    _call(symbol, dtype, device, list(c_args))
 
 
 def _empty(shape, dtype, device):

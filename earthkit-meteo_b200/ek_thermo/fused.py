@@ -56,6 +56,61 @@ def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None):
     return _b.execute_suite("suite_ttdp", (t, td, p), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out)
 
 
+def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False):
+    """The (t, q, p) suite on hybrid model levels with the pressure computed inside the kernel.
+
+    ``t`` and ``q`` are ``[nlev, ...]`` fields, ``sp`` the surface pressure ``[...]``, ``A`` / ``B`` the ``nlev + 1``
+    half-level coefficients.  Equals ``suite_tqp(t, q, p)`` with
+    ``p = earthkit.meteo.vertical.pressure_on_hybrid_levels(A, B, sp, output="full")`` (reference
+    vertical/array/vertical.py:663,708) -- but the ``[nlev, ...]`` pressure array is never written or read:
+    56 instead of 64 bytes per point for the five default outputs.  ``want_p=True`` also returns it (key ``"p"``).
+    """
+    import ctypes
+    from ctypes import c_int, c_int64, c_uint32, c_void_p
+
+    import torch
+
+    outputs = tuple(outputs)
+    slots = _slots(SUITE_TQP_OUTPUTS, outputs)
+    for x in (t, q, sp):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("suite_tq_hybrid: t, q and sp must be torch CUDA tensors")
+    dev = _b._check_device([t, q, sp])
+    dtype = t.dtype
+    if dtype not in (torch.float64, torch.float32) or q.dtype != dtype or sp.dtype != dtype:
+        raise TypeError("suite_tq_hybrid: t, q and sp must share one dtype (float64 or float32)")
+    if t.shape != q.shape or t.dim() < 1 or tuple(t.shape[1:]) != tuple(sp.shape):
+        raise ValueError(f"suite_tq_hybrid: expected t, q of shape (nlev,) + sp.shape, got {tuple(t.shape)}, {tuple(q.shape)}, {tuple(sp.shape)}")
+    nlev, npl = int(t.shape[0]), int(sp.numel())
+    a = torch.as_tensor(A, dtype=dtype, device=dev).contiguous()
+    b = torch.as_tensor(B, dtype=dtype, device=dev).contiguous()
+    if a.numel() != nlev + 1 or b.numel() != nlev + 1:
+        raise ValueError(f"suite_tq_hybrid: A and B need nlev + 1 = {nlev + 1} half-level values")
+    tc, qc, spc = t.contiguous(), q.contiguous(), sp.contiguous()
+    ptrs = (c_void_p * 8)()
+    mask = 0
+    res = {}
+    for name, k in zip(outputs, slots):
+        if out is not None and name in out:
+            o = out[name]
+            if o.dtype != dtype or o.shape != t.shape or not o.is_contiguous() or o.device != dev:
+                raise ValueError(f"suite_tq_hybrid: preallocated output {name!r} must be a contiguous {dtype} tensor of shape {tuple(t.shape)}")
+        else:
+            o = torch.empty_like(tc)
+        res[name] = o
+        ptrs[k] = o.data_ptr()
+        mask |= 1 << k
+    p_ptr = c_void_p(None)
+    if want_p:
+        res["p"] = out["p"] if out is not None and "p" in out else torch.empty_like(tc)
+        p_ptr = c_void_p(res["p"].data_ptr())
+    if npl > 0:
+        _b.call_raw("suite_tq_hybrid", dtype, dev, c_void_p(tc.data_ptr()), c_void_p(qc.data_ptr()), c_void_p(spc.data_ptr()),
+                    c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), c_int(nlev), c_int64(npl), ctypes.cast(ptrs, ctypes.POINTER(c_void_p)),
+                    c_uint32(mask), p_ptr)
+    return res
+
+
 def ept_wet_bulb(t, h, p, humidity="q", ept_method="ifs", t_method="direct", potential=True, want_ept=True, want_wb=True):
     """Equivalent potential temperature and wet-bulb (potential) temperature in one pass.
 

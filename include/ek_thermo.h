@@ -139,6 +139,24 @@ EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const*
 EK_THERMO_FN(ept_wet_bulb, ek_operand t, ek_operand h, ek_operand p, int humidity_kind, int ept_method, int t_method, int at_p0,
              void* ept_out, void* wb_out, int64_t n, void* stream)
 
+/* ---- hybrid (IFS model) levels: the step before the thermo path on model levels -----------
+ * Reference: earthkit.meteo.vertical.pressure_on_hybrid_levels, src/earthkit/meteo/vertical/array/vertical.py:505-737 ("V").
+ * A, B: DEVICE arrays of nhalf half-level coefficients of the dtype; sp: npl surface pressures.
+ * Outputs are [rows, npl], any may be NULL: `full`, `delta`, `alpha` have one row per entry of full_rows (0-based
+ * full-level index k = level number - 1), `half` one row per entry of half_rows (half-level index).  top_k is the
+ * full level treated as the column top (the first level of the computed band, V:645-647), top_toa the field-wide
+ * decision any(p_half[top] <= 0.1 Pa) (V:678; ek_thermo_hybrid_top_is_toa computes it), alpha_top = ln 2 ("ifs")
+ * or 1.0 ("arpege") (V:669). */
+EK_THERMO_FN(pressure_on_hybrid_levels, const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows,
+             int n_full, const int* half_rows, int n_half, int top_k, int top_toa, double alpha_top, void* full, void* half, void* delta,
+             void* alpha, void* stream)
+/* ORs 1 into *flag (a zero-initialised DEVICE int) when any(a_top + b_top * sp <= 0.1) (V:678) */
+EK_THERMO_FN(hybrid_top_is_toa, const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream)
+/* the (t, q, p) suite with p = full-level pressure computed in registers from sp and A/B (nlev + 1 coefficients each);
+ * t, q and every output are [nlev, npl]; p_out (optional) receives the pressure itself */
+EK_THERMO_FN(suite_tq_hybrid, const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,
+             void* const* outs, uint32_t out_mask, void* p_out, void* stream)
+
 /* ---- host-buffer pipeline: the same suite kernel fed from HOST arrays ---------------------------------
  * Streams n points through the GPU in chunks: H2D copy, kernel and D2H copy of successive chunks overlap on
  * `n_slots` internal streams.  Host buffers should be page-locked for full PCIe speed.  `workspace` is a

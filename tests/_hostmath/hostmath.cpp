@@ -89,6 +89,23 @@ extern "C" int hostmath_run(const char* op, int f32, const void* const* ins, con
     EK_CASE("suite_tqp", OpSuiteTQP)
     EK_CASE("suite_ttdp", OpSuiteTTdP)
 #undef EK_CASE
+    if (s == "hyb_full" || s == "hyb_delta_alpha") {  // hybrid-level formulas (ek_thermo_formulas.inc), per point
+        for (int64_t i = 0; i < n; ++i) {
+            auto in = [&](int k) { return f32 ? (double)static_cast<const float*>(ins[k])[i] : static_cast<const double*>(ins[k])[i]; };
+            auto put = [&](int o, double v) {
+                if (!outs[o]) return;
+                if (f32) static_cast<float*>(outs[o])[i] = (float)v; else static_cast<double*>(outs[o])[i] = v;
+            };
+            if (s == "hyb_full") {  // in: a0, b0, a1, b1, sp
+                if (f32) put(0, hyb_full<float>(hyb_half<float>(in(0), in(1), in(4)), hyb_half<float>(in(2), in(3), in(4))));
+                else put(0, hyb_full<double>(hyb_half<double>(in(0), in(1), in(4)), hyb_half<double>(in(2), in(3), in(4))));
+            } else {  // in: ph0, ph1; opt0 = top-is-toa, eps = alpha_top
+                if (f32) { float d, a; hyb_delta_alpha<float>(in(0), in(1), opt0 != 0, (float)eps, d, a); put(0, d); put(1, a); }
+                else { double d, a; hyb_delta_alpha<double>(in(0), in(1), opt0 != 0, eps, d, a); put(0, d); put(1, a); }
+            }
+        }
+        return 0;
+    }
     if (s == "ept_wet_bulb") {
         if (m == EPT_IFS) return ept_wb<EPT_IFS>(tm, f32, ins, scalars, outs, n, P);
         if (m == EPT_BOLTON35) return ept_wb<EPT_BOLTON35>(tm, f32, ins, scalars, outs, n, P);

@@ -11,6 +11,8 @@ oracle/refshim.  Produces, next to this file:
 * ref_live.npz   -- inputs and outputs of the unmodified reference functions for every Case of
                     tests/cases.py on four input sets (seeded random, edge values, the reference's
                     t_hum_p_data.csv grid, the moist-adiabat grid), float64 and float32.
+* ref_hybrid.npz -- hybrid-level pressure: the reference's golden vectors (tests/vertical/_hybrid_core_data.py) and live
+                    outputs of earthkit.meteo.vertical.pressure_on_hybrid_levels.
 * ifs_l137_ab.npz -- the IFS L137 A/B half-level coefficients from the reference's conf JSON (bench input layout).
 * PINNING.json   -- oracle-vs-reference comparison made at generation time (max relative
                     difference and NaN-position mismatches per case).
@@ -95,8 +97,43 @@ def pack_ifs_levels():
     return {"A": np.asarray(d["A"], dtype=np.float64), "B": np.asarray(d["B"], dtype=np.float64)}
 
 
+HYBRID_LEVEL_SETS = {"all": None, "lower": list(range(90, 138)), "reversed": list(range(137, 90, -1)), "two": [2, 1], "top": [1]}
+
+
+def pack_hybrid():
+    """Hybrid-level pressure: the reference's golden vectors (tests/vertical/_hybrid_core_data.py,
+    consumed at tests/vertical/test_array_vertical.py:159-370) and live outputs of the unmodified
+    earthkit.meteo.vertical.pressure_on_hybrid_levels on seeded surface pressures, float64 and float32.
+    Returns (blob, worst oracle-vs-reference difference)."""
+    sys.path.insert(0, os.path.join(REF, "tests", "vertical"))
+    import _hybrid_core_data as D
+    import vertical_oracle as voracle
+    from earthkit.meteo import vertical as ref_vertical
+
+    blob = {"gold/A": np.asarray(D.A, dtype=np.float64), "gold/B": np.asarray(D.B, dtype=np.float64),
+            "gold/p_surf": np.asarray(D.p_surf, dtype=np.float64), "gold/full": np.asarray(D.p_full, dtype=np.float64),
+            "gold/half": np.asarray(D.p_half, dtype=np.float64), "gold/delta": np.asarray(D.delta, dtype=np.float64),
+            "gold/alpha": np.asarray(D.alpha, dtype=np.float64)}
+    rng = np.random.default_rng(17)
+    sp = rng.uniform(4.5e4, 1.06e5, 40)
+    blob["live/sp"] = sp
+    mism = 0
+    for dt in (np.float64, np.float32):
+        a, b, s = (np.asarray(x, dtype=dt) for x in (D.A, D.B, sp))
+        for lname, lv in HYBRID_LEVEL_SETS.items():
+            for at in ("ifs", "arpege"):
+                r = ref_vertical.pressure_on_hybrid_levels(a, b, s, levels=lv, alpha_top=at, output=["full", "half", "delta", "alpha"])
+                o = voracle.pressure_on_hybrid_levels(a, b, s, levels=lv, alpha_top=at, output=["full", "half", "delta", "alpha"])
+                for name, rv, ov in zip(("full", "half", "delta", "alpha"), r, o):
+                    blob[f"live/{np.dtype(dt).name}/{lname}/{at}/{name}"] = rv
+                    mism += int(not (rv.shape == ov.shape and rv.dtype == ov.dtype and np.array_equal(rv, ov, equal_nan=True)))
+    return blob, mism
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "ref_csv.npz"), **pack_csvs())
+    hyb, hyb_mismatch = pack_hybrid()
+    np.savez_compressed(os.path.join(HERE, "ref_hybrid.npz"), **hyb)
     np.savez_compressed(os.path.join(HERE, "ifs_l137_ab.npz"), **pack_ifs_levels())
 
     sets = input_sets()
@@ -133,6 +170,7 @@ def main():
                     if m > 0.0 or nm or infs:  # only deviations are listed; an empty dict = bit-identical
                         pin["cases"][f"{sname}/{dname}/{case.id}/{k}"] = {"max_rel": m, "nan_mismatch": nm, "inf_mismatch": infs}
     pin["summary"] = {"worst_max_rel": worst, "nan_or_inf_mismatches": nan_mismatch, "n_entries": n_entries}
+    pin["hybrid"] = {"arrays_not_bit_identical_to_reference": hyb_mismatch, "n_arrays": sum(k.startswith("live/float") for k in hyb)}
     np.savez_compressed(os.path.join(HERE, "ref_live.npz"), **blob)
     with open(os.path.join(HERE, "PINNING.json"), "w") as f:
         json.dump(pin, f, indent=1, sort_keys=True)

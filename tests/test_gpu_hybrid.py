@@ -1,0 +1,129 @@
+"""GPU parity of the hybrid-level kernels through the C ABI: against the oracle, the reference's
+golden vectors, the live-reference fixtures, and -- for the fused kernel -- against suite_tqp fed with the
+materialised pressure."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import thermo_oracle as oracle
+import vertical_oracle as voracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUTS = ("full", "half", "delta", "alpha")
+LEVEL_SETS = {"all": None, "lower": list(range(90, 138)), "reversed": list(range(137, 90, -1)), "two": [2, 1], "top": [1]}
+
+
+@pytest.fixture(scope="module")
+def hyb():
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hybrid.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _tol(name, f32):
+    # delta/alpha difference quotients lose digits where ph1 - ph0 << ph0 (thin top layers); float32 as the reference's
+    # own tolerance table (tests/vertical/test_array_vertical.py:196-203)
+    if f32:
+        return {"full": (2e-6, 0), "half": (2e-6, 0), "delta": (1e-4, 1e-6), "alpha": (2e-3, 1e-4)}[name]
+    return {"full": (1e-14, 0), "half": (1e-14, 0), "delta": (1e-12, 0), "alpha": (1e-9, 1e-13)}[name]
+
+
+def test_reference_golden_vectors(hyb):
+    from ek_thermo import vertical
+
+    sp = torch.from_numpy(hyb["gold/p_surf"]).to(DEV)
+    res = vertical.pressure_on_hybrid_levels(hyb["gold/A"], hyb["gold/B"], sp, output=list(OUTS))
+    for name, r in zip(OUTS, res):
+        np.testing.assert_allclose(r.cpu().numpy(), hyb[f"gold/{name}"], rtol=1e-6, atol=1e-8, err_msg=name)  # the reference test's tolerance
+
+
+@pytest.mark.parametrize("dname", ["float64", "float32"])
+def test_live_reference_fixtures(hyb, dname):
+    from ek_thermo import vertical
+
+    dt = np.dtype(dname).type
+    sp = torch.from_numpy(hyb["live/sp"].astype(dt)).to(DEV)
+    for lname, lv in LEVEL_SETS.items():
+        for at in ("ifs", "arpege"):
+            res = vertical.pressure_on_hybrid_levels(hyb["gold/A"], hyb["gold/B"], sp, levels=lv, alpha_top=at, output=list(OUTS))
+            for name, r in zip(OUTS, res):
+                want = hyb[f"live/{dname}/{lname}/{at}/{name}"]
+                rtol, atol = _tol(name, dname == "float32")
+                np.testing.assert_allclose(r.cpu().numpy().astype(np.float64), want.astype(np.float64), rtol=rtol, atol=atol, err_msg=f"{lname}/{at}/{name}")
+
+
+@pytest.mark.parametrize("shape", [(1001,), (37, 53), (6, 8, 16)])
+def test_against_oracle_shapes_outputs_axis(hyb, shape):
+    from ek_thermo import vertical
+
+    rng = np.random.default_rng(5)
+    sp = rng.uniform(4.8e4, 1.07e5, shape)
+    d = torch.from_numpy(sp).to(DEV)
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    for output in ("full", "half", ["delta", "alpha"], ["half", "full"], list(OUTS)):
+        for va in (0, -1):
+            got = vertical.pressure_on_hybrid_levels(a, b, d, output=output, vertical_axis=va)
+            want = voracle.pressure_on_hybrid_levels(a, b, sp, output=output, vertical_axis=va)
+            got = got if isinstance(got, tuple) else (got,)
+            want = want if isinstance(want, tuple) else (want,)
+            names = (output,) if isinstance(output, str) else output
+            for name, g, w in zip(names, got, want):
+                assert tuple(g.shape) == w.shape
+                rtol, atol = _tol(name, False)
+                np.testing.assert_allclose(g.cpu().numpy(), w, rtol=rtol, atol=atol, err_msg=f"{output}/{va}/{name}")
+    # unaligned view of sp (scalar ld/st path) and an empty field
+    got = vertical.pressure_on_hybrid_levels(a, b, d.reshape(-1)[1:], output="full")
+    np.testing.assert_allclose(got.cpu().numpy(), voracle.pressure_on_hybrid_levels(a, b, sp.reshape(-1)[1:]), rtol=1e-14)
+    assert vertical.pressure_on_hybrid_levels(a, b, d.reshape(-1)[:0]).shape == (137, 0)
+
+
+def test_top_of_atmosphere_decision_is_field_wide():
+    """V:678: if ANY point has p_half[top] <= 0.1 Pa, every point uses the TOA form for the top layer."""
+    from ek_thermo import vertical
+
+    a = np.array([0.05, 50.0, 500.0, 0.0])
+    b = np.array([1.0e-6, 1.0e-3, 0.3, 1.0])  # top half-level pressure = 0.05 + 1e-6 * sp: <= 0.1 only for sp <= 5e4
+    for sp in (np.array([6.0e4, 9.0e4, 1.0e5]), np.array([6.0e4, 4.0e4, 1.0e5])):
+        for at in ("ifs", "arpege"):
+            got = vertical.pressure_on_hybrid_levels(a, b, torch.from_numpy(sp).to(DEV), alpha_top=at, output=["delta", "alpha"])
+            want = voracle.pressure_on_hybrid_levels(a, b, sp, alpha_top=at, output=["delta", "alpha"])
+            for g, w in zip(got, want):
+                np.testing.assert_allclose(g.cpu().numpy(), w, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("npl", [4096 * 3, 10007])
+def test_fused_suite_equals_materialised_pressure(hyb, dtype, npl):
+    from ek_thermo import fused, vertical
+
+    rng = np.random.default_rng(9)
+    nlev = 137
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    sp = rng.uniform(5.0e4, 1.05e5, npl).astype(dtype)
+    p_ref = voracle.pressure_on_hybrid_levels(a.astype(dtype), b.astype(dtype), sp)
+    t = np.clip(288.15 * (p_ref.astype(np.float64) / 101325.0) ** 0.19 + rng.uniform(-15, 15, (nlev, npl)), 180, 320).astype(dtype)
+    q = rng.uniform(1e-6, 0.02, (nlev, npl)).astype(dtype)
+    dt_, dq, dsp = (torch.from_numpy(x).to(DEV) for x in (t, q, sp))
+    f32 = dtype == np.float32
+    names = tuple(fused.SUITE_TQP_OUTPUTS)
+    got = fused.suite_tq_hybrid(dt_, dq, dsp, a, b, outputs=names, want_p=True)
+    p_dev = vertical.pressure_on_hybrid_levels(a, b, dsp)
+    torch.testing.assert_close(got["p"], p_dev, rtol=0, atol=0)  # same formula, same kernel family: bit-identical
+    np.testing.assert_allclose(got["p"].cpu().numpy(), p_ref, rtol=2e-6 if f32 else 1e-14)
+    two_step = fused.suite_tqp(dt_, dq, p_dev, outputs=names)
+    with np.errstate(all="ignore"):
+        want = oracle.suite_tqp(t, q, p_ref)
+    for name in names:
+        torch.testing.assert_close(got[name], two_step[name], rtol=1e-5 if f32 else 1e-14, atol=0, equal_nan=True, msg=name)
+        g = got[name].cpu().numpy().astype(np.float64)
+        w = np.asarray(want[name]).astype(np.float64)
+        bad = np.abs(g - w) > (2e-5 if f32 else 1e-12) * np.abs(w)
+        assert bad.mean() <= (0.01 if f32 else 0.0), (name, np.abs(g - w).max())
+    # default five outputs (compile-time mask) and preallocated buffers
+    out = {"theta": torch.empty_like(dt_)}
+    five = fused.suite_tq_hybrid(dt_, dq, dsp, a, b, out=out)
+    assert five["theta"].data_ptr() == out["theta"].data_ptr() and set(five) == set(fused.DEFAULT_TQP)
+    for name in fused.DEFAULT_TQP:
+        torch.testing.assert_close(five[name], got[name], rtol=1e-5 if f32 else 1e-14, atol=0, equal_nan=True, msg=name)

@@ -1,0 +1,114 @@
+"""Hybrid-level pressure, CPU side: the oracle against the reference's golden vectors and the
+live-reference fixtures; the per-point formulas the kernels use (g++ build) against the oracle; the wrapper's
+argument errors."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import hostmath_backend
+import vertical_oracle as voracle
+
+LEVEL_SETS = {"all": None, "lower": list(range(90, 138)), "reversed": list(range(137, 90, -1)), "two": [2, 1], "top": [1]}
+OUTS = ("full", "half", "delta", "alpha")
+
+
+@pytest.fixture(scope="module")
+def hyb():
+    import os
+
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hybrid.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_oracle_matches_reference_golden_vectors(hyb):
+    """tests/vertical/_hybrid_core_data.py, with the reference test's tolerances (atol 1e-8, rtol 1e-6; TT vertical :159-215)."""
+    res = voracle.pressure_on_hybrid_levels(hyb["gold/A"], hyb["gold/B"], hyb["gold/p_surf"], output=list(OUTS))
+    for name, r in zip(OUTS, res):
+        np.testing.assert_allclose(r, hyb[f"gold/{name}"], rtol=1e-6, atol=1e-8, err_msg=name)
+
+
+@pytest.mark.parametrize("dname", ["float64", "float32"])
+def test_oracle_bit_identical_to_live_reference(hyb, dname):
+    dt = np.dtype(dname).type
+    a, b, sp = (hyb[k].astype(dt) for k in ("gold/A", "gold/B", "live/sp"))
+    for lname, lv in LEVEL_SETS.items():
+        for at in ("ifs", "arpege"):
+            res = voracle.pressure_on_hybrid_levels(a, b, sp, levels=lv, alpha_top=at, output=list(OUTS))
+            for name, r in zip(OUTS, res):
+                want = hyb[f"live/{dname}/{lname}/{at}/{name}"]
+                assert r.dtype == want.dtype and r.shape == want.shape
+                np.testing.assert_allclose(r, want, rtol=8 * np.finfo(want.dtype).eps, atol=0, err_msg=f"{lname}/{at}/{name}")
+
+
+def test_oracle_errors():
+    a, b, sp = np.arange(4.0), np.arange(4.0), np.ones(3)
+    for kw in (dict(output=[]), dict(output="x"), dict(alpha_top="x"), dict(levels=[4]), dict(levels=[0])):
+        with pytest.raises(ValueError):
+            voracle.pressure_on_hybrid_levels(a, b, sp, **kw)
+
+
+def _host(op, ins, n_out, dtype, opt0=0, eps=0.0):
+    lib = hostmath_backend.lib()
+    n = ins[0].size
+    arr = [np.ascontiguousarray(x.astype(dtype)) for x in ins]
+    outs = [np.empty(n, dtype=dtype) for _ in range(n_out)]
+    pin = (ctypes.c_void_p * len(arr))(*[x.ctypes.data for x in arr])
+    sc = (ctypes.c_double * len(arr))()
+    pout = (ctypes.c_void_p * n_out)(*[x.ctypes.data for x in outs])
+    rc = lib.hostmath_run(op.encode(), int(dtype == np.float32), pin, sc, pout, n, opt0, 0, eps, 1, 0, 0)
+    assert rc == 0
+    return outs
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_per_point_formulas_match_oracle(hyb, dtype):
+    """hyb_half / hyb_full / hyb_delta_alpha of ek_thermo_formulas.inc (what the kernels execute per point)."""
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    sp = hyb["live/sp"]
+    nlev = a.size - 1
+    k = np.repeat(np.arange(nlev), sp.size)
+    spp = np.tile(sp, nlev)
+    full, half, delta, alpha = voracle.pressure_on_hybrid_levels(a.astype(dtype), b.astype(dtype), sp.astype(dtype), output=list(OUTS))
+    rtol = 1e-13 if dtype == np.float64 else 2e-6
+    got = _host("hyb_full", [a[k], b[k], a[k + 1], b[k + 1], spp], 1, dtype)[0]
+    np.testing.assert_allclose(got, full.ravel(), rtol=rtol)
+    ph0, ph1 = half[:-1].ravel(), half[1:].ravel()
+    for top, at in ((0, 0.0), (1, np.log(2.0)), (1, 1.0)):
+        d, al = _host("hyb_delta_alpha", [ph0, ph1], 2, dtype, opt0=top, eps=at)
+        if top:
+            np.testing.assert_allclose(d, np.log(ph1.astype(dtype) / dtype(0.1)), rtol=rtol * 10)
+            np.testing.assert_allclose(al, at, rtol=rtol)
+        else:
+            sel = k >= 1  # the top layer of this coefficient set is the TOA special case in the oracle
+            np.testing.assert_allclose(d[sel], delta.ravel()[sel], rtol=2e-5 if dtype == np.float32 else 1e-12)
+            np.testing.assert_allclose(al[sel], alpha.ravel()[sel], rtol=2e-3 if dtype == np.float32 else 1e-9)
+
+
+def test_wrapper_argument_errors(monkeypatch):
+    import ek_thermo
+    from ek_thermo import fused, vertical
+
+    a = b = [0.0, 1.0, 2.0, 3.0]
+    sp_cpu = torch.ones(5, dtype=torch.float64)
+    with pytest.raises(ValueError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu, output=[])
+    with pytest.raises(ValueError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu, output="nope")
+    with pytest.raises(ValueError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu, alpha_top="nope")
+    with pytest.raises(TypeError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu)  # CPU tensor: no CPU path
+    with pytest.raises(TypeError):
+        vertical.pressure_on_hybrid_levels(a, b, np.ones(5))
+    monkeypatch.setattr(ek_thermo._backend, "_check_device", lambda tensors: tensors[0].device)
+    with pytest.raises(ValueError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu, levels=[4])
+    with pytest.raises(ValueError):
+        vertical.pressure_on_hybrid_levels(a, b, sp_cpu, levels=[0])
+    t = torch.ones(3, 5, dtype=torch.float64)
+    with pytest.raises(ValueError):
+        fused.suite_tq_hybrid(t, t, sp_cpu, a[:3], b[:3])  # needs nlev + 1 coefficients
+    with pytest.raises(ValueError):
+        fused.suite_tq_hybrid(t, t, torch.ones(4, dtype=torch.float64), a, b)  # sp shape mismatch
