@@ -16,6 +16,12 @@
 
 using namespace ek;
 
+#if EK_LEAN_MATH
+#define EK_FAST_NS fastm
+#else
+#define EK_FAST_NS exactm
+#endif
+
 // levels whose t/q loads are in flight per thread.  Measured on B200 (O1280 x 137, fp64): 2 -> 10.3-11.0 ms,
 // 3 -> 12.0 ms, 4 -> 13.9 ms (register pressure at the 64-register cap), so 2.
 #ifndef EK_HYB_LU
@@ -210,6 +216,89 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) suite_hybrid_kernel(con
     }
 }
 
+struct GeoArgs {
+    const void *t, *q;           // [nlev, npl], level 0 = top of the band
+    const void *sp, *A, *B;      // computed alpha/delta: surface pressure + half-level coefficients of the WHOLE model
+    const void *alpha, *delta;   // given alpha/delta: [nlev, npl]
+    const void* zs;              // surface geopotential [npl] (modes that need it)
+    void* out;                   // [nlev, npl]
+    int nlev;
+    int64_t npl;
+    int band0;     // half-level index of the band's top (model levels - nlev)
+    int top_toa;   // field-wide any(p_half[band0] <= 0.1) (V:678)
+    double alpha_top;
+    int mode;      // HeightMode
+};
+
+// One thread walks VEC columns from the bottom level to the top one: d = R(q) t, dphi_k = sum_{j>k} d_j delta_j + d_k alpha_k
+// (V:799-810, same accumulation order as the reference's flipped cumulative sum).  alpha/delta come from registers
+// (sp, A, B) or from memory (GIVEN_AD).  Loads of two levels are in flight before the math of the lower one.
+template <typename T, bool GIVEN_AD, bool VECOK>
+__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) column_geopotential_kernel(const GeoArgs g) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int TILE = kThreads * VEC;
+    constexpr int NARR = GIVEN_AD ? 4 : 2;
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8) lean::init_tables();
+#endif
+    const T* A = static_cast<const T*>(g.A);
+    const T* B = static_cast<const T*>(g.B);
+    const T* arr[4] = {static_cast<const T*>(g.t), static_cast<const T*>(g.q), static_cast<const T*>(g.alpha), static_cast<const T*>(g.delta)};
+    const int64_t ptiles = (g.npl + TILE - 1) / TILE;
+    for (int64_t pt = blockIdx.x; pt < ptiles; pt += gridDim.x) {
+        const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
+        if (i0 >= g.npl) continue;
+        T sp[VEC], zs[VEC], hs[VEC], sum[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sp[j] = zs[j] = hs[j] = sum[j] = T(0);
+        if (!GIVEN_AD) ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+        if (g.zs != nullptr) ld_row<T, VECOK>(static_cast<const T*>(g.zs), i0, g.npl, zs, false);
+        if (g.mode == EK_HM_GEOM_GROUND) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) hs[j] = EK_FAST_NS::geom_from_z(zs[j]);
+        }
+        for (int k = g.nlev - 1; k >= 0; k -= 2) {
+            T x[2][NARR][VEC];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (k - u >= 0) {
+#pragma unroll
+                    for (int c = 0; c < NARR; ++c) ld_row<T, VECOK>(arr[c] + (int64_t)(k - u) * g.npl, i0, g.npl, x[u][c], true);
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int kk = k - u;
+                if (kk < 0) break;
+                T a0 = T(0), b0 = T(0), a1 = T(0), b1 = T(0);
+                if (!GIVEN_AD) {
+                    a0 = __ldg(A + g.band0 + kk), b0 = __ldg(B + g.band0 + kk), a1 = __ldg(A + g.band0 + kk + 1), b1 = __ldg(B + g.band0 + kk + 1);
+                }
+                const bool top = g.top_toa && kk == 0;
+                T y[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    T al, de;
+                    if (GIVEN_AD) {
+                        al = x[u][2][j];
+                        de = x[u][3][j];
+                    } else {
+                        delta_alpha<T>(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]), top, static_cast<T>(g.alpha_top), de, al);
+                    }
+                    const T d = exactm::gas_constant(x[u][1][j]) * x[u][0][j];
+                    const T dphi = (kk == g.nlev - 1) ? d * al : sum[j] + d * al;  // V:808-809
+                    sum[j] = (kk == g.nlev - 1) ? d * de : sum[j] + d * de;        // V:804 (running sum of d * delta below this layer)
+                    T h = EK_FAST_NS::height_output(dphi, zs[j], hs[j], g.mode);
+#if EK_LEAN_DEVICE
+                    if (sizeof(T) == 8 && __builtin_expect(is_nan_bits(h), 0)) h = exactm::height_output(dphi, zs[j], exactm::geom_from_z(zs[j]), g.mode);
+#endif
+                    y[j] = h;
+                }
+                st_row<T, VECOK>(static_cast<T*>(g.out) + (int64_t)kk * g.npl, i0, g.npl, y);
+            }
+        }
+    }
+}
+
 int grid_for(int64_t items) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return -1;
@@ -280,6 +369,40 @@ static int impl_hybrid_top_is_toa(const void* sp, int64_t npl, double a_top, dou
     return EK_OK;
 }
 EK_API(hybrid_top_is_toa, (const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream), (sp, npl, a_top, b_top, flag, stream))
+
+template <typename T>
+static int impl_geopotential_on_hybrid_levels(const void* t, const void* q, int nlev, int64_t npl, const void* sp, const void* A, const void* B,
+                                              int nhalf, int top_toa, double alpha_top, const void* alpha, const void* delta, const void* zs,
+                                              int mode, void* out, void* stream) {
+    const char* what = "geopotential_on_hybrid_levels";
+    const bool given = alpha != nullptr || delta != nullptr;
+    if (!t || !q || !out || nlev < 1 || npl < 0 || mode < 0 || mode > 5) return set_error(EK_ERR_ARG, "%s: bad arguments", what);
+    if (given && (!alpha || !delta)) return set_error(EK_ERR_ARG, "%s: alpha and delta must be given together", what);
+    if (!given && (!sp || !A || !B || nhalf < nlev + 1)) return set_error(EK_ERR_ARG, "%s: sp, A, B (>= nlev + 1 half-levels) are required", what);
+    if ((mode == 1 || mode == 2 || mode == 4 || mode == 5) && !zs) return set_error(EK_ERR_ARG, "%s: this output needs the surface geopotential zs", what);
+    if (npl == 0) return EK_OK;
+    GeoArgs g{t, q, sp, A, B, alpha, delta, zs, out, nlev, npl, given ? 0 : nhalf - 1 - nlev, top_toa, alpha_top, mode};
+    constexpr int TILE = kThreads * Vec16<T>::N;
+    const int blocks = grid_for((npl + TILE - 1) / TILE);
+    if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
+    const bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(alpha) && ok16(delta) && ok16(zs) && ok16(out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (given) {
+        if (vec) column_geopotential_kernel<T, true, true><<<blocks, kThreads, kSmemBytes, st>>>(g);
+        else column_geopotential_kernel<T, true, false><<<blocks, kThreads, kSmemBytes, st>>>(g);
+    } else {
+        if (vec) column_geopotential_kernel<T, false, true><<<blocks, kThreads, kSmemBytes, st>>>(g);
+        else column_geopotential_kernel<T, false, false><<<blocks, kThreads, kSmemBytes, st>>>(g);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    return EK_OK;
+}
+EK_API(geopotential_on_hybrid_levels,
+       (const void* t, const void* q, int nlev, int64_t npl, const void* sp, const void* A, const void* B, int nhalf, int top_toa,
+        double alpha_top, const void* alpha, const void* delta, const void* zs, int mode, void* out, void* stream),
+       (t, q, nlev, npl, sp, A, B, nhalf, top_toa, alpha_top, alpha, delta, zs, mode, out, stream))
 
 template <template <uint32_t> class OpM, template <uint32_t> class OpME, typename T>
 static int suite_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs,

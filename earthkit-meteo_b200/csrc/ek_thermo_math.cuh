@@ -56,6 +56,7 @@ struct Consts {
     double wa0, wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4, inv_t0;  // wbpt "direct" rational fit (T:1051-1052)
     double k10, k11, k12, k20, k21, k22, dD1, dD0, c121, c266, c058, c04;  // Davies-Jones first guess (T:1090-1128)
     double t_start, eps_default, neg_lambda, hundred, hundredth, c800, inv_800;
+    double g, inv_g, R_earth;  // constants.py:53,57 (height conversions, vertical.py:330-502)
 };
 
 namespace cdef {
@@ -138,6 +139,9 @@ constexpr Consts make_consts() {
     k.hundredth = 0.01;
     k.c800 = 800.0;
     k.inv_800 = 1.0 / 800.0;
+    k.g = 9.80665;
+    k.inv_g = 1.0 / 9.80665;
+    k.R_earth = 6371229.0;
     return k;
 }
 

@@ -24,6 +24,17 @@ def _coeff_tensors(A, B, dtype, device):
     return a, b
 
 
+def _top_is_toa(a, b, top_half, spc, dtype, dev):
+    """V:678: does ANY point have p_half[top] <= 0.1 Pa?  A constant when B[top] == 0, else a one-flag reduction kernel."""
+    a_top, b_top = float(a[top_half]), float(b[top_half])
+    if b_top == 0.0 or spc.numel() == 0:
+        return int(a_top <= 0.1)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    _b.call_raw("hybrid_top_is_toa", dtype, dev, c_void_p(spc.data_ptr()), c_int64(spc.numel()), c_double(a_top), c_double(b_top),
+                c_void_p(flag.data_ptr()))
+    return int(flag.item())
+
+
 def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="full", vertical_axis=0):
     """Pressure on full / half levels, ``delta`` and ``alpha`` of hybrid levels.  Reference V:505-737.
 
@@ -62,14 +73,7 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
     npl = spc.numel()
     top_toa = 0
     if "delta" in want or "alpha" in want:  # V:678: one decision for the whole field
-        a_top, b_top = float(a[top_k]), float(b[top_k])
-        if b_top == 0.0 or npl == 0:
-            top_toa = int(a_top <= 0.1)
-        else:
-            flag = torch.zeros(1, dtype=torch.int32, device=dev)
-            _b.call_raw("hybrid_top_is_toa", dtype, dev, c_void_p(spc.data_ptr()), c_int64(npl), c_double(a_top), c_double(b_top),
-                        c_void_p(flag.data_ptr()))
-            top_toa = int(flag.item())
+        top_toa = _top_is_toa(a, b, top_k, spc, dtype, dev)
     rows_f = torch.tensor(full_rows, dtype=torch.int32, device=dev)
     rows_h = torch.tensor(half_rows, dtype=torch.int32, device=dev)
     res = {}
@@ -87,3 +91,92 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
     if vertical_axis != 0 and outs[0].dim() > 1:  # V:731-733
         outs = [r.movedim(0, vertical_axis) for r in outs]
     return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# geopotential thickness / geopotential / height on hybrid levels (V:741-1188)
+# --------------------------------------------------------------------------------------------------------------------
+_HM = {"thickness": 0, "geopotential": 1, ("geopotential", "sea"): 2, ("geopotential", "ground"): 3, ("geometric", "sea"): 4,
+       ("geometric", "ground"): 5}
+
+
+def _column_kernel(t, q, mode, vertical_axis, sp=None, A=None, B=None, alpha_top="ifs", alpha=None, delta=None, zs=None):
+    for x in (t, q):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("ek_thermo.vertical: t and q must be torch CUDA tensors (no CPU path)")
+    tensors = [x for x in (t, q, sp, alpha, delta, zs) if isinstance(x, torch.Tensor)]
+    dev = _b._check_device(tensors)
+    dtype = t.dtype if t.dtype in (torch.float64, torch.float32) else torch.float64
+    if t.shape != q.shape or t.dim() < 1:
+        raise ValueError(f"t and q must have the same shape, got {tuple(t.shape)} and {tuple(q.shape)}")
+    if vertical_axis != 0:  # V:878-883: work with the vertical axis first
+        t, q = t.movedim(vertical_axis, 0), q.movedim(vertical_axis, 0)
+        if alpha is not None:
+            alpha, delta = alpha.movedim(vertical_axis, 0), delta.movedim(vertical_axis, 0)
+    tc, qc = t.to(dtype).contiguous(), q.to(dtype).contiguous()
+    nlev = int(tc.shape[0])
+    col_shape = tuple(tc.shape[1:])
+    npl = int(tc[0].numel()) if nlev else 0
+    null = c_void_p(None)
+    keep = []
+
+    def col(x, name):  # a per-column field (sp, zs): broadcast to the column shape
+        x = torch.as_tensor(x, dtype=dtype, device=dev)
+        if tuple(x.shape) != col_shape:
+            x = x.expand(col_shape)
+        x = x.contiguous()
+        keep.append(x)
+        return c_void_p(x.data_ptr())
+
+    p_sp = p_a = p_b = p_al = p_de = p_zs = null
+    nhalf = top_toa = 0
+    if alpha is not None:
+        if alpha.shape != t.shape or delta.shape != t.shape:
+            raise ValueError("alpha and delta must have the shape of t")
+        ac, dc = alpha.to(dtype).contiguous(), delta.to(dtype).contiguous()
+        keep += [ac, dc]
+        p_al, p_de = c_void_p(ac.data_ptr()), c_void_p(dc.data_ptr())
+    else:
+        if alpha_top not in ("ifs", "arpege"):
+            raise ValueError(f"Unknown method '{alpha_top}' for pressure calculation. Use 'ifs' or 'arpege'.")
+        a, b = _coeff_tensors(A, B, dtype, dev)
+        nhalf = a.numel()
+        if nlev > nhalf - 1:
+            raise ValueError(f"Requested level {nlev} exceeds the maximum number of levels {nhalf - 1}.")
+        keep += [a, b]
+        p_a, p_b, p_sp = c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), col(sp, "sp")
+        top_toa = _top_is_toa(a, b, nhalf - 1 - nlev, keep[-1], dtype, dev)  # the band is the nlev bottom-most levels (V:1191-1203)
+    if mode in (1, 2, 4, 5):
+        p_zs = col(zs, "zs")
+    out = torch.empty_like(tc)
+    if npl > 0 and nlev > 0:
+        _b.call_raw("geopotential_on_hybrid_levels", dtype, dev, c_void_p(tc.data_ptr()), c_void_p(qc.data_ptr()), c_int(nlev), c_int64(npl),
+                    p_sp, p_a, p_b, c_int(nhalf), c_int(top_toa), c_double(math.log(2.0) if alpha_top == "ifs" else 1.0), p_al, p_de, p_zs,
+                    c_int(mode), c_void_p(out.data_ptr()))
+    del keep
+    return out.movedim(0, vertical_axis) if vertical_axis != 0 else out
+
+
+def relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, alpha, delta, vertical_axis=0):
+    """Geopotential thickness between the surface and the full levels, from precomputed alpha/delta.  Reference V:815-891."""
+    return _column_kernel(t, q, 0, vertical_axis, alpha=alpha, delta=delta)
+
+
+def relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp, alpha_top="ifs", vertical_axis=0):
+    """Same, with alpha/delta computed inside the kernel from sp and A/B (never materialised).  Reference V:894-994.
+
+    ``t``/``q`` may hold only the bottom-most contiguous levels of the model (V:1191-1203)."""
+    return _column_kernel(t, q, 0, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top)
+
+
+def geopotential_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", vertical_axis=0):
+    """Geopotential on the full levels: thickness + surface geopotential, one kernel.  Reference V:997-1069."""
+    return _column_kernel(t, q, 1, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top, zs=zs)
+
+
+def height_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", h_type="geometric", h_reference="ground", vertical_axis=0):
+    """Geometric / geopotential height above sea level / ground, one kernel.  Reference V:1072-1188."""
+    if h_reference not in ["sea", "ground"]:
+        raise ValueError(f"Unknown '{h_reference=}'. Use 'sea' or 'ground'.")  # V:1163-1164
+    mode = _HM[("geometric" if h_type == "geometric" else "geopotential", h_reference)]  # any other h_type -> geopotential (V:1175-1186)
+    return _column_kernel(t, q, mode, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top, zs=zs)

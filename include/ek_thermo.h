@@ -152,6 +152,16 @@ EK_THERMO_FN(pressure_on_hybrid_levels, const void* A, const void* B, int nhalf,
              void* alpha, void* stream)
 /* ORs 1 into *flag (a zero-initialised DEVICE int) when any(a_top + b_top * sp <= 0.1) (V:678) */
 EK_THERMO_FN(hybrid_top_is_toa, const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream)
+/* geopotential thickness / geopotential / height of hybrid full levels (V:741-1188): d = R(q) t per
+ * layer and a bottom-up running sum along the level axis, one thread per column.  t, q, out: [nlev, npl] with level 0 the
+ * top of the band; the band is the nlev BOTTOM-most model levels (V:1191-1203).  alpha/delta are computed in registers
+ * from sp and the nhalf half-level coefficients A, B -- or read from memory when `alpha` and `delta` are non-NULL
+ * (then sp/A/B may be NULL).  mode: 0 thickness, 1 geopotential (+ zs), 2 geopotential height above sea ((dphi+zs)/g),
+ * 3 geopotential height above ground (dphi/g), 4 geometric height above sea, 5 geometric height above ground. */
+enum { EK_HM_THICKNESS = 0, EK_HM_GEOPOTENTIAL = 1, EK_HM_GH_SEA = 2, EK_HM_GH_GROUND = 3, EK_HM_GEOM_SEA = 4, EK_HM_GEOM_GROUND = 5 };
+EK_THERMO_FN(geopotential_on_hybrid_levels, const void* t, const void* q, int nlev, int64_t npl, const void* sp, const void* A,
+             const void* B, int nhalf, int top_toa, double alpha_top, const void* alpha, const void* delta, const void* zs, int mode,
+             void* out, void* stream)
 /* the (t, q, p) suite with p = full-level pressure computed in registers from sp and A/B (nlev + 1 coefficients each);
  * t, q and every output are [nlev, npl]; p_out (optional) receives the pressure itself */
 EK_THERMO_FN(suite_tq_hybrid, const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,

@@ -73,3 +73,81 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
     if vertical_axis != 0 and outs[0].ndim > 1:  # V:731-733
         outs = [np.moveaxis(r, 0, vertical_axis) for r in outs]
     return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+# --------------------------------------------------------------------------------------------------
+# geopotential thickness / geopotential / height on hybrid levels -- the in-tree consumer of
+# thermo.specific_gas_constant (V:798-801): R(q) * t, then a bottom-up cumulative sum along the level axis.
+# --------------------------------------------------------------------------------------------------
+G = 9.80665  # constants.g (constants.py:53)
+R_EARTH = 6371229  # constants.R_earth (constants.py:57)
+RD, RV = 287.0597, 461.51  # constants.py:22,26
+
+
+def geopotential_height_from_geopotential(z):
+    """V:330-354"""
+    return z / G
+
+
+def geometric_height_from_geopotential(z, R_earth=R_EARTH):
+    """V:472-502"""
+    z = z / G
+    return R_earth * z / (R_earth - z)
+
+
+def _thickness(t, q, alpha, delta):
+    """V:741-812 (_compute_relative_geopotential_thickness_on_hybrid_levels), vertical axis first."""
+    R = RD + (RV - RD) * q  # thermo.specific_gas_constant (T:1706)
+    d = R * t
+    dphi_half = np.cumulative_sum(np.flip(d[1:, ...] * delta[1:, ...], axis=0), axis=0)  # V:804
+    dphi_half = np.flip(dphi_half, axis=0)
+    dphi = np.zeros_like(d)
+    dphi[:-1, ...] = dphi_half + d[:-1, ...] * alpha[:-1, ...]  # V:808
+    dphi[-1, ...] = d[-1, ...] * alpha[-1, ...]  # V:809
+    return dphi
+
+
+def relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, alpha, delta, vertical_axis=0):
+    """V:815-891"""
+    t, q, alpha, delta = (np.asarray(x) for x in (t, q, alpha, delta))
+    if vertical_axis != 0:
+        t, q, alpha, delta = (np.moveaxis(x, vertical_axis, 0) for x in (t, q, alpha, delta))
+    dphi = _thickness(t, q, alpha, delta)
+    return np.moveaxis(dphi, 0, vertical_axis) if vertical_axis != 0 else dphi
+
+
+def _hybrid_subset(data, A, vertical_axis=0):
+    """V:1191-1203: data on fewer levels than A/B describe = the bottom-most contiguous band."""
+    nlev_t, nlev = data.shape[vertical_axis], A.shape[0] - 1
+    return None if nlev_t == nlev else list(range(nlev - nlev_t + 1, nlev + 1))
+
+
+def relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp, alpha_top="ifs", vertical_axis=0):
+    """V:894-994"""
+    t, q, A, B, sp = (np.asarray(x) for x in (t, q, A, B, sp))
+    levels = _hybrid_subset(t, A, vertical_axis)
+    alpha, delta = pressure_on_hybrid_levels(A, B, sp, alpha_top=alpha_top, levels=levels, output=("alpha", "delta"))
+    if vertical_axis != 0:  # V:981-986 (alpha/delta are moved too, exactly as the reference does)
+        alpha, delta, t, q = (np.moveaxis(x, vertical_axis, 0) for x in (alpha, delta, t, q))
+    dphi = _thickness(t, q, alpha, delta)
+    return np.moveaxis(dphi, 0, vertical_axis) if vertical_axis != 0 else dphi
+
+
+def geopotential_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", vertical_axis=0):
+    """V:997-1069"""
+    z = relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp, vertical_axis=vertical_axis, alpha_top=alpha_top)
+    return z + np.asarray(zs)
+
+
+def height_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", h_type="geometric", h_reference="ground", vertical_axis=0):
+    """V:1072-1188"""
+    if h_reference not in ["sea", "ground"]:
+        raise ValueError(f"Unknown '{h_reference=}'. Use 'sea' or 'ground'.")
+    z_thickness = relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp, alpha_top=alpha_top, vertical_axis=vertical_axis)
+    if h_reference == "sea":
+        z = z_thickness + np.asarray(zs)
+        return geometric_height_from_geopotential(z) if h_type == "geometric" else geopotential_height_from_geopotential(z)
+    if h_type == "geometric":
+        zs = np.asarray(zs)
+        return geometric_height_from_geopotential(z_thickness + zs) - geometric_height_from_geopotential(zs)
+    return geopotential_height_from_geopotential(z_thickness)

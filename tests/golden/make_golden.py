@@ -127,6 +127,41 @@ def pack_hybrid():
                 for name, rv, ov in zip(("full", "half", "delta", "alpha"), r, o):
                     blob[f"live/{np.dtype(dt).name}/{lname}/{at}/{name}"] = rv
                     mism += int(not (rv.shape == ov.shape and rv.dtype == ov.dtype and np.array_equal(rv, ov, equal_nan=True)))
+    # --- geopotential thickness / geopotential / height on hybrid levels ------------------------
+    import _hybrid_height_data as H
+
+    blob.update({"gold/t": np.asarray(D.t, dtype=np.float64), "gold/q": np.asarray(D.q, dtype=np.float64),
+                 "gold/z": np.asarray(D.z, dtype=np.float64)})
+    for k in ("A", "B", "t", "q", "z_surf", "p_surf", "h_geopotential_sea", "h_geopotential_ground", "h_geometric_sea", "h_geometric_ground"):
+        blob[f"goldh/{k}"] = np.asarray(getattr(H, k), dtype=np.float64)
+    npt = 24
+    sp2 = rng.uniform(5.0e4, 1.05e5, npt)
+    zs2 = rng.uniform(-500.0, 3.0e4, npt)
+    pf = ref_vertical.pressure_on_hybrid_levels(np.asarray(D.A), np.asarray(D.B), sp2)
+    t2 = np.clip(288.15 * (pf / 101325.0) ** 0.19 + rng.uniform(-10, 10, pf.shape), 180.0, 320.0)
+    q2 = rng.uniform(1e-6, 0.02, pf.shape)
+    blob.update({"geo/sp": sp2, "geo/zs": zs2, "geo/t": t2, "geo/q": q2})
+    for dt in (np.float64, np.float32):
+        dn = np.dtype(dt).name
+        a, b, s_, z_, tt, qq = (np.asarray(x, dtype=dt) for x in (D.A, D.B, sp2, zs2, t2, q2))
+        for part, sl in (("all", slice(None)), ("lower", slice(90, None))):
+            for at in ("ifs", "arpege"):
+                calls = {
+                    "thickness": lambda m: m.relative_geopotential_thickness_on_hybrid_levels(tt[sl], qq[sl], a, b, s_, alpha_top=at),
+                    "geopotential": lambda m: m.geopotential_on_hybrid_levels(tt[sl], qq[sl], z_, a, b, s_, alpha_top=at),
+                }
+                for ht in ("geometric", "geopotential"):
+                    for hr in ("sea", "ground"):
+                        calls[f"h_{ht}_{hr}"] = (lambda m, ht=ht, hr=hr: m.height_on_hybrid_levels(tt[sl], qq[sl], z_, a, b, s_, alpha_top=at, h_type=ht, h_reference=hr))
+                for name, fn in calls.items():
+                    rv, ov = fn(ref_vertical), fn(voracle)
+                    blob[f"geo/{dn}/{part}/{at}/{name}"] = rv
+                    mism += int(not (rv.shape == ov.shape and rv.dtype == ov.dtype and np.array_equal(rv, ov, equal_nan=True)))
+        al, de = ref_vertical.pressure_on_hybrid_levels(a, b, s_, output=("alpha", "delta"))
+        rv = ref_vertical.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(tt, qq, al, de)
+        ov = voracle.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(tt, qq, al, de)
+        blob[f"geo/{dn}/from_alpha_delta"] = rv
+        mism += int(not np.array_equal(rv, ov, equal_nan=True))
     return blob, mism
 
 
@@ -170,7 +205,7 @@ def main():
                     if m > 0.0 or nm or infs:  # only deviations are listed; an empty dict = bit-identical
                         pin["cases"][f"{sname}/{dname}/{case.id}/{k}"] = {"max_rel": m, "nan_mismatch": nm, "inf_mismatch": infs}
     pin["summary"] = {"worst_max_rel": worst, "nan_or_inf_mismatches": nan_mismatch, "n_entries": n_entries}
-    pin["hybrid"] = {"arrays_not_bit_identical_to_reference": hyb_mismatch, "n_arrays": sum(k.startswith("live/float") for k in hyb)}
+    pin["hybrid"] = {"arrays_not_bit_identical_to_reference": hyb_mismatch, "n_arrays": sum(k.startswith("live/float") or k.startswith("geo/float") for k in hyb)}
     np.savez_compressed(os.path.join(HERE, "ref_live.npz"), **blob)
     with open(os.path.join(HERE, "PINNING.json"), "w") as f:
         json.dump(pin, f, indent=1, sort_keys=True)

@@ -127,3 +127,75 @@ def test_fused_suite_equals_materialised_pressure(hyb, dtype, npl):
     assert five["theta"].data_ptr() == out["theta"].data_ptr() and set(five) == set(fused.DEFAULT_TQP)
     for name in fused.DEFAULT_TQP:
         torch.testing.assert_close(five[name], got[name], rtol=1e-5 if f32 else 1e-14, atol=0, equal_nan=True, msg=name)
+
+
+# ---- geopotential thickness / geopotential / height on hybrid levels --------------------------------
+from test_hybrid_cpu import GEO_NAMES, geo_call  # noqa: E402
+
+
+def test_geopotential_reference_golden_vectors(hyb):
+    """The reference's own vectors and tolerances (tests/vertical/test_array_vertical.py:385-520)."""
+    from ek_thermo import vertical
+
+    d = lambda k: torch.from_numpy(hyb[k]).to(DEV)  # noqa: E731
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    t, q, sp, z = d("gold/t"), d("gold/q"), d("gold/p_surf"), hyb["gold/z"]
+    close = lambda got, want: np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-8)  # noqa: E731
+    close(vertical.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, d("gold/alpha"), d("gold/delta")), z)
+    close(vertical.relative_geopotential_thickness_on_hybrid_levels(t, q, a, b, sp), z)
+    close(vertical.relative_geopotential_thickness_on_hybrid_levels(t[90:], q[90:], a, b, sp), z[90:])
+    close(vertical.geopotential_on_hybrid_levels(t, q, torch.zeros(2, device=DEV, dtype=torch.float64), a, b, sp), z)
+    a, b = hyb["goldh/A"], hyb["goldh/B"]
+    t, q, sp, zs = d("goldh/t"), d("goldh/q"), d("goldh/p_surf"), d("goldh/z_surf")
+    for ht in ("geometric", "geopotential"):
+        for hr in ("sea", "ground"):
+            close(vertical.height_on_hybrid_levels(t, q, zs, a, b, sp, h_type=ht, h_reference=hr), hyb[f"goldh/h_{ht}_{hr}"])
+
+
+@pytest.mark.parametrize("dname", ["float64", "float32"])
+def test_geopotential_live_reference_fixtures(hyb, dname):
+    from ek_thermo import vertical
+
+    dt = np.dtype(dname).type
+    f32 = dname == "float32"
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    sp, zs, t, q = (torch.from_numpy(hyb[k].astype(dt)).to(DEV) for k in ("geo/sp", "geo/zs", "geo/t", "geo/q"))
+    for part, sl in (("all", slice(None)), ("lower", slice(90, None))):
+        for at in ("ifs", "arpege"):
+            for name in GEO_NAMES:
+                got = geo_call(vertical, name, t[sl], q[sl], zs, a, b, sp, at).cpu().numpy().astype(np.float64)
+                want = hyb[f"geo/{dname}/{part}/{at}/{name}"].astype(np.float64)
+                # float32: the reference itself keeps alpha/delta in float64 there; its own test allows atol 10 (m2/s2)
+                np.testing.assert_allclose(got, want, rtol=2e-5 if f32 else 1e-12, atol=10.0 if f32 else 1e-7, err_msg=f"{part}/{at}/{name}")
+    al, de = vertical.pressure_on_hybrid_levels(a, b, sp, output=("alpha", "delta"))
+    got = vertical.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, al, de)
+    np.testing.assert_allclose(got.cpu().numpy().astype(np.float64), hyb[f"geo/{dname}/from_alpha_delta"].astype(np.float64),
+                               rtol=2e-5 if f32 else 1e-12, atol=10.0 if f32 else 1e-7)
+
+
+@pytest.mark.parametrize("shape", [(3001,), (17, 20)])
+def test_geopotential_against_oracle(hyb, shape):
+    """Columns of any shape, odd sizes (scalar ld/st path), vertical_axis, and the thickness identities."""
+    from ek_thermo import vertical
+
+    rng = np.random.default_rng(31)
+    a, b = hyb["gold/A"], hyb["gold/B"]
+    sp = rng.uniform(5.0e4, 1.06e5, shape)
+    zs = rng.uniform(-400.0, 4.0e4, shape)
+    pf = voracle.pressure_on_hybrid_levels(a, b, sp)
+    t = np.clip(288.15 * (pf / 101325.0) ** 0.19 + rng.uniform(-12, 12, pf.shape), 180.0, 320.0)
+    q = rng.uniform(1e-6, 0.02, pf.shape)
+    dsp, dzs, dt_, dq = (torch.from_numpy(x).to(DEV) for x in (sp, zs, t, q))
+    for name in GEO_NAMES:
+        got = geo_call(vertical, name, dt_, dq, dzs, a, b, dsp, "ifs")
+        want = geo_call(voracle, name, t, q, zs, a, b, sp, "ifs")
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-12, atol=1e-7, err_msg=name)
+    # vertical axis last (the sensible meaning; the reference's own moveaxis of alpha/delta is only consistent for axis 0)
+    thick = vertical.relative_geopotential_thickness_on_hybrid_levels(dt_, dq, a, b, dsp)
+    last = vertical.relative_geopotential_thickness_on_hybrid_levels(dt_.movedim(0, -1).contiguous(), dq.movedim(0, -1).contiguous(), a, b, dsp,
+                                                                     vertical_axis=-1)
+    torch.testing.assert_close(last.movedim(-1, 0), thick, rtol=0, atol=0)
+    # identities: geopotential = thickness + zs; thickness decreases towards the surface and is positive
+    geo = vertical.geopotential_on_hybrid_levels(dt_, dq, dzs, a, b, dsp)
+    torch.testing.assert_close(geo, thick + dzs, rtol=1e-15, atol=1e-9)
+    assert bool((thick[:-1] > thick[1:]).all()) and bool((thick[-1] > 0).all())

@@ -112,3 +112,65 @@ def test_wrapper_argument_errors(monkeypatch):
         fused.suite_tq_hybrid(t, t, sp_cpu, a[:3], b[:3])  # needs nlev + 1 coefficients
     with pytest.raises(ValueError):
         fused.suite_tq_hybrid(t, t, torch.ones(4, dtype=torch.float64), a, b)  # sp shape mismatch
+
+
+# ---- geopotential thickness / geopotential / height on hybrid levels --------------------------------
+def test_geopotential_oracle_matches_reference_golden_vectors(hyb):
+    """tests/vertical/test_array_vertical.py:385-520 (atol 1e-8, rtol 1e-6)."""
+    a, b, sp, t, q, z = (hyb[f"gold/{k}"] for k in ("A", "B", "p_surf", "t", "q", "z"))
+    np.testing.assert_allclose(voracle.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, hyb["gold/alpha"], hyb["gold/delta"]),
+                               z, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(voracle.relative_geopotential_thickness_on_hybrid_levels(t, q, a, b, sp), z, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(voracle.relative_geopotential_thickness_on_hybrid_levels(t[90:], q[90:], a, b, sp), z[90:], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(voracle.geopotential_on_hybrid_levels(t, q, np.zeros(2), a, b, sp), z, rtol=1e-6, atol=1e-8)
+    a, b, sp, t, q, zs = (hyb[f"goldh/{k}"] for k in ("A", "B", "p_surf", "t", "q", "z_surf"))
+    for ht in ("geometric", "geopotential"):
+        for hr in ("sea", "ground"):
+            got = voracle.height_on_hybrid_levels(t, q, zs, a, b, sp, h_type=ht, h_reference=hr)
+            np.testing.assert_allclose(got, hyb[f"goldh/h_{ht}_{hr}"], rtol=1e-6, atol=1e-8, err_msg=f"{ht}/{hr}")
+    with pytest.raises(ValueError):
+        voracle.height_on_hybrid_levels(t, q, zs, a, b, sp, h_reference="moon")
+
+
+GEO_NAMES = ("thickness", "geopotential", "h_geometric_sea", "h_geometric_ground", "h_geopotential_sea", "h_geopotential_ground")
+
+
+def geo_call(mod, name, t, q, zs, a, b, sp, at):
+    if name == "thickness":
+        return mod.relative_geopotential_thickness_on_hybrid_levels(t, q, a, b, sp, alpha_top=at)
+    if name == "geopotential":
+        return mod.geopotential_on_hybrid_levels(t, q, zs, a, b, sp, alpha_top=at)
+    _, ht, hr = name.split("_")
+    return mod.height_on_hybrid_levels(t, q, zs, a, b, sp, alpha_top=at, h_type=ht, h_reference=hr)
+
+
+@pytest.mark.parametrize("dname", ["float64", "float32"])
+def test_geopotential_oracle_bit_identical_to_live_reference(hyb, dname):
+    dt = np.dtype(dname).type
+    a, b, sp, zs, t, q = (hyb[k].astype(dt) for k in ("gold/A", "gold/B", "geo/sp", "geo/zs", "geo/t", "geo/q"))
+    for part, sl in (("all", slice(None)), ("lower", slice(90, None))):
+        for at in ("ifs", "arpege"):
+            for name in GEO_NAMES:
+                got = geo_call(voracle, name, t[sl], q[sl], zs, a, b, sp, at)
+                want = hyb[f"geo/{dname}/{part}/{at}/{name}"]
+                assert got.dtype == want.dtype and got.shape == want.shape
+                np.testing.assert_allclose(got, want, rtol=64 * np.finfo(want.dtype).eps, atol=0, err_msg=f"{part}/{at}/{name}")
+
+
+def test_geopotential_wrapper_errors(monkeypatch):
+    import ek_thermo
+    from ek_thermo import vertical
+
+    t = torch.ones(3, 5, dtype=torch.float64)
+    a = b = [0.0, 1.0, 2.0, 3.0]
+    with pytest.raises(ValueError):
+        vertical.height_on_hybrid_levels(t, t, t[0], a, b, t[0], h_reference="moon")
+    with pytest.raises(TypeError):
+        vertical.relative_geopotential_thickness_on_hybrid_levels(t, t, a, b, t[0])  # CPU tensors: no CPU path
+    monkeypatch.setattr(ek_thermo._backend, "_check_device", lambda tensors: tensors[0].device)
+    with pytest.raises(ValueError):
+        vertical.relative_geopotential_thickness_on_hybrid_levels(t, t, a[:3], b[:3], t[0])  # more data levels than A/B describe
+    with pytest.raises(ValueError):
+        vertical.relative_geopotential_thickness_on_hybrid_levels(t, t, a, b, t[0], alpha_top="nope")
+    with pytest.raises(ValueError):
+        vertical.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, t, t[:2], t[:2])
