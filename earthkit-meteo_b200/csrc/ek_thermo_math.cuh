@@ -57,6 +57,7 @@ struct Consts {
     double k10, k11, k12, k20, k21, k22, dD1, dD0, c121, c266, c058, c04;  // Davies-Jones first guess (T:1090-1128)
     double t_start, eps_default, neg_lambda, hundred, hundredth, c800, inv_800;
     double g, inv_g, R_earth;  // constants.py:53,57 (height conversions, vertical.py:330-502)
+    double degree, radian, two_omega, neg_Rd_g, minus_pi2, pi15;  // wind (constants.py:60-78, wind/array/wind.py)
 };
 
 namespace cdef {
@@ -142,6 +143,18 @@ constexpr Consts make_consts() {
     k.g = 9.80665;
     k.inv_g = 1.0 / 9.80665;
     k.R_earth = 6371229.0;
+    // constants.py:60-78, evaluated in the order Python evaluates them
+    constexpr double pi = 3.141592653589793;  // numpy.pi
+    constexpr double solar_day = 86400;
+    constexpr double sideral_year = 365.25 * solar_day * 2 * pi / 6.283076;
+    constexpr double sideral_day = solar_day / (1.0 + solar_day / sideral_year);
+    constexpr double omega = 2.0 * pi / sideral_day;
+    k.degree = 180.0 / pi;
+    k.radian = 1.0 / (180.0 / pi);
+    k.two_omega = 2 * omega;                      // wind.py:251
+    k.neg_Rd_g = -cdef::Rd / 9.80665;             // wind.py:222
+    k.minus_pi2 = -pi / 2.0;                      // wind.py:42
+    k.pi15 = 1.5 * pi;                            // wind.py:48
     return k;
 }
 
@@ -164,6 +177,15 @@ EK_HD double m_log_exact(double x) { return ::log(x); }
 EK_HD float m_log_exact(float x) { return ::logf(x); }
 EK_HD double m_pow_exact(double x, double y) { return ::pow(x, y); }
 EK_HD float m_pow_exact(float x, float y) { return ::powf(x, y); }
+
+EK_HD double m_hypot(double x, double y) { return ::hypot(x, y); }
+EK_HD float m_hypot(float x, float y) { return ::hypotf(x, y); }
+EK_HD double m_atan2(double y, double x) { return ::atan2(y, x); }
+EK_HD float m_atan2(float y, float x) { return ::atan2f(y, x); }
+EK_HD double m_sin(double x) { return ::sin(x); }
+EK_HD float m_sin(float x) { return ::sinf(x); }
+EK_HD double m_cos(double x) { return ::cos(x); }
+EK_HD float m_cos(float x) { return ::cosf(x); }
 
 template <typename T> EK_HD T m_nan() { return static_cast<T>(NAN); }
 template <typename T> EK_HD T sq(T x) { return x * x; }

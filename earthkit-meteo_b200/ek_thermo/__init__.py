@@ -9,7 +9,7 @@
 Importing this package loads libek_thermo.so and fails loudly if it has not been built: there is no
 CPU or eager-PyTorch fallback anywhere.
 """
-from . import _backend, fused, hostpipe, partition, thermo, vertical  # noqa: F401
+from . import _backend, fused, hostpipe, partition, thermo, vertical, wind  # noqa: F401
 from ._backend import EkThermoError, launch_count, set_launch_config, version  # noqa: F401
 
-__all__ = ["thermo", "vertical", "fused", "partition", "hostpipe", "version", "launch_count", "set_launch_config", "EkThermoError"]
+__all__ = ["thermo", "vertical", "wind", "fused", "partition", "hostpipe", "version", "launch_count", "set_launch_config", "EkThermoError"]

@@ -83,6 +83,13 @@ SIGNATURES = {
     "wet_bulb_potential_temperature_from_dewpoint": (3, (c_int, c_int), 1),
     "wet_bulb_potential_temperature_from_specific_humidity": (3, (c_int, c_int), 1),
     "ept_wet_bulb": (3, (c_int, c_int, c_int, c_int), 2),
+    # wind
+    "wind_speed": (2, (), 1),
+    "wind_direction": (2, (c_int, c_int), 1),
+    "wind_xy_to_polar": (2, (c_int,), 2),
+    "wind_polar_to_xy": (2, (c_int,), 2),
+    "w_from_omega": (3, (), 1),
+    "coriolis": (1, (), 1),
 }
 
 for _name, (_nin, _opts, _nout) in SIGNATURES.items():

@@ -139,6 +139,16 @@ EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const*
 EK_THERMO_FN(ept_wet_bulb, ek_operand t, ek_operand h, ek_operand p, int humidity_kind, int ept_method, int t_method, int at_p0,
              void* ept_out, void* wb_out, int64_t n, void* stream)
 
+/* ---- wind: the elementwise functions of earthkit.meteo.wind (src/earthkit/meteo/wind/array/wind.py "W") ----
+ * convention: 0 = "meteo", 1 = "polar" (W:99-104, W:184-189) */
+enum { EK_WIND_METEO = 0, EK_WIND_POLAR = 1 };
+EK_THERMO_FN(wind_speed, ek_operand u, ek_operand v, void* out, int64_t n, void* stream)                                       /* W:15-34 */
+EK_THERMO_FN(wind_direction, ek_operand u, ek_operand v, int convention, int to_positive, void* out, int64_t n, void* stream)  /* W:64-104 */
+EK_THERMO_FN(wind_xy_to_polar, ek_operand x, ek_operand y, int convention, void* speed_out, void* direction_out, int64_t n, void* stream) /* W:107-135 */
+EK_THERMO_FN(wind_polar_to_xy, ek_operand magnitude, ek_operand direction, int convention, void* x_out, void* y_out, int64_t n, void* stream) /* W:156-189 */
+EK_THERMO_FN(w_from_omega, ek_operand omega, ek_operand t, ek_operand p, void* out, int64_t n, void* stream)                   /* W:192-222 */
+EK_THERMO_FN(coriolis, ek_operand lat, void* out, int64_t n, void* stream)                                                     /* W:225-251 */
+
 /* ---- hybrid (IFS model) levels: the step before the thermo path on model levels -----------
  * Reference: earthkit.meteo.vertical.pressure_on_hybrid_levels, src/earthkit/meteo/vertical/array/vertical.py:505-737 ("V").
  * A, B: DEVICE arrays of nhalf half-level coefficients of the dtype; sp: npl surface pressures.

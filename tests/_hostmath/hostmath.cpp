@@ -86,6 +86,12 @@ extern "C" int hostmath_run(const char* op, int f32, const void* const* ins, con
     EK_CASE("lcl_temperature", OpLclT)
     EK_CASE("lcl", OpLcl)
     EK_CASE("specific_gas_constant", OpGasConstant)
+    EK_CASE("wind_speed", OpWindSpeed)
+    EK_CASE("wind_direction", OpWindDirection)
+    EK_CASE("wind_xy_to_polar", OpXyToPolar)
+    EK_CASE("wind_polar_to_xy", OpPolarToXy)
+    EK_CASE("w_from_omega", OpWFromOmega)
+    EK_CASE("coriolis", OpCoriolis)
     EK_CASE("suite_tqp", OpSuiteTQP)
     EK_CASE("suite_ttdp", OpSuiteTTdP)
 #undef EK_CASE

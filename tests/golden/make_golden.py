@@ -13,6 +13,7 @@ oracle/refshim.  Produces, next to this file:
                     t_hum_p_data.csv grid, the moist-adiabat grid), float64 and float32.
 * ref_hybrid.npz -- hybrid-level pressure: the reference's golden vectors (tests/vertical/_hybrid_core_data.py) and live
                     outputs of earthkit.meteo.vertical.pressure_on_hybrid_levels.
+* ref_wind.npz   -- live outputs of the reference's elementwise wind functions.
 * ifs_l137_ab.npz -- the IFS L137 A/B half-level coefficients from the reference's conf JSON (bench input layout).
 * PINNING.json   -- oracle-vs-reference comparison made at generation time (max relative
                     difference and NaN-position mismatches per case).
@@ -165,8 +166,60 @@ def pack_hybrid():
     return blob, mism
 
 
+WIND_CASES = [  # (function, argument names, kwargs)
+    ("speed", ("u", "v"), {}),
+    ("direction", ("u", "v"), {"convention": "meteo"}),
+    ("direction", ("u", "v"), {"convention": "polar"}),
+    ("direction", ("u", "v"), {"convention": "polar", "to_positive": False}),
+    ("xy_to_polar", ("u", "v"), {"convention": "meteo"}),
+    ("xy_to_polar", ("u", "v"), {"convention": "polar"}),
+    ("polar_to_xy", ("mag", "dir"), {"convention": "meteo"}),
+    ("polar_to_xy", ("mag", "dir"), {"convention": "polar"}),
+    ("w_from_omega", ("omega", "t", "p"), {}),
+    ("coriolis", ("lat",), {}),
+]
+
+
+def wind_case_id(fn, kwargs):
+    return fn + "".join(f";{k}={v}" for k, v in sorted(kwargs.items()))
+
+
+def wind_inputs(n=600, seed=23):
+    rng = np.random.default_rng(seed)
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.nan, np.inf, -np.inf, 1e-300, 1e300, 25.0, -12.5])
+    u = np.concatenate([rng.normal(0, 12, n), special[rng.integers(0, special.size, 60)], [0, 1, 1, 1, 0, -1, -1, -1, 0, np.nan, 1, np.nan]])
+    v = np.concatenate([rng.normal(0, 12, n), special[rng.integers(0, special.size, 60)], [1, 1, 0, -1, -1, -1, 0, 1, 0, 1, np.nan, np.nan]])
+    m = u.size
+    return dict(u=u, v=v, mag=np.abs(rng.normal(8, 6, m)), dir=rng.uniform(-90, 450, m), omega=rng.normal(0, 2, m),
+                t=rng.uniform(200, 320, m), p=rng.uniform(1e3, 1.05e5, m), lat=rng.uniform(-90, 90, m))
+
+
+def pack_wind():
+    """live outputs of the unmodified earthkit.meteo.wind elementwise functions (float64 and float32)."""
+    import wind_oracle as woracle
+    from earthkit.meteo import wind as ref_wind
+
+    inp = wind_inputs()
+    blob = {f"in/{k}": v for k, v in inp.items()}
+    mism = 0
+    for dt in (np.float64, np.float32):
+        for fn, args, kw in WIND_CASES:
+            a = [inp[x].astype(dt) for x in args]
+            with np.errstate(all="ignore"):
+                r, o = getattr(ref_wind, fn)(*a, **kw), getattr(woracle, fn)(*a, **kw)
+            r = r if isinstance(r, tuple) else (r,)
+            o = o if isinstance(o, tuple) else (o,)
+            for k, (rv, ov) in enumerate(zip(r, o)):
+                rv = np.asarray(rv)
+                blob[f"out/{np.dtype(dt).name}/{wind_case_id(fn, kw)}/{k}"] = rv
+                mism += int(not (rv.shape == np.shape(ov) and rv.dtype == np.asarray(ov).dtype and np.array_equal(rv, ov, equal_nan=True)))
+    return blob, mism
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "ref_csv.npz"), **pack_csvs())
+    wind_blob, wind_mismatch = pack_wind()
+    np.savez_compressed(os.path.join(HERE, "ref_wind.npz"), **wind_blob)
     hyb, hyb_mismatch = pack_hybrid()
     np.savez_compressed(os.path.join(HERE, "ref_hybrid.npz"), **hyb)
     np.savez_compressed(os.path.join(HERE, "ifs_l137_ab.npz"), **pack_ifs_levels())
@@ -205,6 +258,7 @@ def main():
                     if m > 0.0 or nm or infs:  # only deviations are listed; an empty dict = bit-identical
                         pin["cases"][f"{sname}/{dname}/{case.id}/{k}"] = {"max_rel": m, "nan_mismatch": nm, "inf_mismatch": infs}
     pin["summary"] = {"worst_max_rel": worst, "nan_or_inf_mismatches": nan_mismatch, "n_entries": n_entries}
+    pin["wind"] = {"arrays_not_bit_identical_to_reference": wind_mismatch, "n_arrays": sum(k.startswith("out/") for k in wind_blob)}
     pin["hybrid"] = {"arrays_not_bit_identical_to_reference": hyb_mismatch, "n_arrays": sum(k.startswith("live/float") or k.startswith("geo/float") for k in hyb)}
     np.savez_compressed(os.path.join(HERE, "ref_live.npz"), **blob)
     with open(os.path.join(HERE, "PINNING.json"), "w") as f:

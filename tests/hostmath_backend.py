@@ -72,6 +72,10 @@ def fake_call(symbol, dtype, device, c_args):
     elif symbol in ("saturation_vapour_pressure", "saturation_vapour_pressure_slope", "saturation_mixing_ratio",
                     "saturation_specific_humidity", "lcl_temperature", "lcl"):
         kw = dict(opt0=opts[0])
+    elif symbol == "wind_direction":
+        kw = dict(opt0=opts[0], opt1=opts[1])
+    elif symbol in ("wind_xy_to_polar", "wind_polar_to_xy"):
+        kw = dict(opt0=opts[0])
     elif symbol in ("saturation_mixing_ratio_slope", "saturation_specific_humidity_slope"):
         kw = dict(opt0=opts[2], opt1=opts[0] | (opts[1] << 1), eps=opts[3])
     elif symbol in ("ept_from_dewpoint", "ept_from_specific_humidity"):
