@@ -442,3 +442,31 @@ def test_exact_build_variant_passes_the_same_parity_cases():
                         "(oracle_random and f64) or (oracle_edge and f64) or fixtures or csv_goldens or fused_suites"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_cuda_graph_capture_and_replay(ek):
+    """Every entry point is a plain asynchronous launch on the caller's stream (no allocation, no sync inside the
+    library), so a call sequence can be captured into a CUDA graph -- the way to run the launch-latency-bound
+    ERA5-level case (BASELINE.json configs[0], 1 038 240 points) without per-call host overhead."""
+    from ek_thermo import fused
+
+    n = 721 * 1440
+    inp = random_inputs(n, seed=41)
+    t, q, p = (torch.from_numpy(inp[k]).to(DEV) for k in ("t", "q", "p"))
+    out = {k: torch.empty_like(t) for k in ("theta", "rh")}
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fused.suite_tqp(t, q, p, outputs=("theta", "rh"), out=out)  # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fused.suite_tqp(t, q, p, outputs=("theta", "rh"), out=out)
+    for o in out.values():
+        o.zero_()
+    t.add_(1.5)  # new input values in the captured buffers
+    g.replay()
+    torch.cuda.synchronize()
+    tn = inp["t"] + 1.5
+    np.testing.assert_allclose(out["theta"].cpu().numpy(), oracle.potential_temperature(tn, inp["p"]), rtol=1e-12)
+    np.testing.assert_allclose(out["rh"].cpu().numpy(), oracle.relative_humidity_from_specific_humidity(tn, inp["q"], inp["p"]), rtol=1e-12)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ctas", default="16")
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="also time the fused suites replayed from a CUDA graph")
     ap.add_argument("--realistic", action="store_true", help="IFS-like smooth t(p) instead of uniform random t")
     a = ap.parse_args()
     dt = torch.float64 if a.dtype == "f64" else torch.float32
@@ -88,7 +89,21 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             gbs = narr * esz * n / ms / 1e6
-            print(f"ctas/SM={ctas:3d} {name:22s} {ms:8.3f} ms  {n / ms / 1e6:8.2f} Gpt/s  {gbs:8.1f} GB/s  frac={gbs / peak:.3f}")
+            extra = ""
+            if a.graph and name.startswith("suite"):  # the same call replayed from a CUDA graph (no host work per call)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    fn()
+                for _ in range(3):
+                    gr.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(a.iters):
+                    gr.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                extra = f"  graph-replay {e0.elapsed_time(e1) / a.iters * 1e3:7.2f} us/call"
+            print(f"ctas/SM={ctas:3d} {name:22s} {ms:8.3f} ms  {n / ms / 1e6:8.2f} Gpt/s  {gbs:8.1f} GB/s  frac={gbs / peak:.3f}{extra}")
 
 
 if __name__ == "__main__":
