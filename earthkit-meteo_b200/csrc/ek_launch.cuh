@@ -27,18 +27,15 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     InArgs<Op::NIN> in;
     OutArgs<Op::NOUT> out;
     int vec_ok = 1;
-    bool any_array = false;
     for (int k = 0; k < Op::NIN; ++k) {
         in.p[k] = ins[k].ptr;
         in.s[k] = ins[k].value;
         if (ins[k].ptr) {
-            any_array = true;
             if (!aligned16(ins[k].ptr)) vec_ok = 0;
             if (reinterpret_cast<uintptr_t>(ins[k].ptr) % sizeof(T))
                 return set_error(EK_ERR_ARG, "%s: input %d is not aligned to its element size", what, k);
         }
     }
-    (void)any_array;
     uint32_t mask = 0;
     for (int o = 0; o < Op::NOUT; ++o) {
         out.p[o] = outs[o];
@@ -72,7 +69,6 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
 }
 
 inline bool valid_phase(int v) { return v >= 0 && v <= 2; }
-inline bool valid_ept(int v) { return v >= 0 && v <= 2; }
 
 // defines ek_thermo_<NAME>_f64 / _f32 forwarding to the template function impl_<NAME><T>
 #define EK_API(NAME, PARAMS, ARGS)                                                    \

@@ -7,7 +7,10 @@
 //     flight per SM to cover HBM latency (needs ~35 KB/SM in flight at 6.5 TB/s);
 //   * all intermediates of a point live in registers; outputs are stored as soon as a vector is done;
 //   * tiles are handed to CTAs round-robin (grid-stride), grid sized as SMs x CTAs-per-SM;
-//   * no shared memory, no TMA, no tensor cores: there is nothing to stage or contract.
+//   * no shared-memory staging, no TMA, no tensor cores: there is nothing to stage or contract (shared memory only
+//     holds the 2.5 KB log/exp tables of the lean math, ek_thermo_lean.cuh);
+//   * every point goes through the fast (lean-math) functor; a point whose result contains a NaN is recomputed by
+//     the exact functor in an out-of-line cold path, so special values behave exactly as the reference.
 // Broadcast scalars arrive by value (never materialised); unaligned views use scalar ld/st inside the
 // same kernel (uniform branch), and the sub-tile tail is a scalar grid-stride loop.
 #pragma once
