@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 O1280_POINTS = 4 * 1280 * 1289  # 6 599 680 (octahedral reduced Gaussian grid O1280)
 N_LEVELS = 137
-METRIC = "thermo grid-points/s (fused suite theta,es,rh,td,Tv; achieved HBM GB/s vs roofline in `roofline`)"
+METRIC = "thermo grid-points/s"  # BASELINE.json metric; the achieved HBM GB/s vs roofline half of it is the `roofline` object
 
 WORKLOADS = {
     # name: (kind, outputs, levels, points per level, dtype)

@@ -3,8 +3,10 @@
 
     python tools/sweep.py [--dtype f64] [--max-bytes 1.2e11] > gpurun_out/sweep.jsonl
 
-Per-GPU numbers; with G GPUs the field is cut into G contiguous shards (ek_thermo.partition) that run
-independently, so the aggregate is G x the per-GPU figure at N/G points (no collective).
+Single process: per-GPU numbers.  Under torchrun (`python -m torch.distributed.run --nproc-per-node G tools/sweep.py`)
+the field of N points is cut into G contiguous shards (ek_thermo.partition), every rank runs its shard on its own
+GPU, and rank 0 prints the aggregate: N / max-over-ranks of the device time (NCCL only carries the barrier and that
+max; there is no data-path collective).
 Small N is launch-latency bound (Python call + ~5 us launch); the table shows where the roofline regime starts.
 """
 import argparse
@@ -17,7 +19,7 @@ sys.path[:0] = [os.path.join(ROOT, "earthkit-meteo_b200")]
 
 import torch  # noqa: E402
 
-from ek_thermo import fused, thermo  # noqa: E402
+from ek_thermo import fused, partition, thermo  # noqa: E402
 
 
 def main():
@@ -27,15 +29,26 @@ def main():
     a = ap.parse_args()
     dt = torch.float64 if a.dtype == "f64" else torch.float32
     esz = 8 if a.dtype == "f64" else 4
-    dev = "cuda:0"
+    rank, world, local = partition.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     sizes = [1_000_000, 3_000_000, 10_000_000, 30_000_000, 100_000_000, 300_000_000, 1_000_000_000, 3_000_000_000, 10_000_000_000]
     g = torch.Generator(device=dev).manual_seed(0)
-    for n in sizes:
+    for n_total in sizes:
+        b, e = partition.shard_range(n_total, world, rank, align=4096)
+        n = e - b
         kernels = {"theta": 3, "rh_from_q": 4, "suite_tqp5": 8}
         for name, narr in kernels.items():
-            if narr * esz * n > a.max_bytes:
-                print(json.dumps({"n": n, "kernel": name, "dtype": a.dtype, "skipped": "exceeds the per-GPU memory cap; shard it (ek_thermo.partition)"}), flush=True)
+            if narr * esz * (n_total // world + 4096) > a.max_bytes:
+                if rank == 0:
+                    print(json.dumps({"n": n_total, "gpus": world, "kernel": name, "dtype": a.dtype,
+                                      "skipped": "exceeds the per-GPU memory cap; shard it over more GPUs (ek_thermo.partition)"}), flush=True)
                 continue
             t = torch.empty(n, device=dev, dtype=dt).uniform_(200.0, 320.0, generator=g)
             p = torch.empty(n, device=dev, dtype=dt).uniform_(1.0e3, 1.05e5, generator=g)
@@ -48,11 +61,13 @@ def main():
             else:
                 out = {k: torch.empty_like(t) for k in fused.DEFAULT_TQP}
                 fn = lambda: fused.suite_tqp(t, q, p, out=out)  # noqa: E731
-            iters = max(5, min(2000, int(2e9 / n)))
+            iters = max(5, min(2000, int(2e9 / max(n, 1))))
             # rotate over several buffers when the working set would sit in the 126 MB L2
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(iters):
@@ -60,11 +75,19 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
-            gbs = narr * esz * n / ms / 1e6
-            print(json.dumps({"n": n, "kernel": name, "dtype": a.dtype, "ms": round(ms, 5), "gpts": round(n / ms / 1e6, 3), "gbs": round(gbs, 1),
-                              "frac_of_measured_hbm": round(gbs / peak, 4), "in_L2": narr * esz * n < 126e6, "iters": iters}), flush=True)
+            if dist is not None:
+                tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            gbs = narr * esz * n_total / ms / 1e6
+            if rank == 0:
+                print(json.dumps({"n": n_total, "gpus": world, "kernel": name, "dtype": a.dtype, "ms": round(ms, 5),
+                                  "gpts": round(n_total / ms / 1e6, 3), "gbs": round(gbs, 1),
+                                  "frac_of_measured_hbm": round(gbs / (peak * world), 4), "in_L2": narr * esz * n < 126e6, "iters": iters}), flush=True)
             del t, p, q, out
             torch.cuda.empty_cache()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
