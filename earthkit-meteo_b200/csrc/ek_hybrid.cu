@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) suite_hybrid_kernel(con
                 for (int j = 0; j < VEC; ++j) {
                     pf[j] = exactm::hyb_full(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]));
                     T a[3] = {x[u][0][j], x[u][1][j], pf[j]}, r[S_NSLOTS];
-                    point<Op, OpE, T>(a, r, P);
+                    point<Op, OpE, T>(a, r, P, 3u);  // t and q are the array inputs; p is derived
 #pragma unroll
                     for (int o = 0; o < S_NSLOTS; ++o) y[o][j] = r[o];
                 }

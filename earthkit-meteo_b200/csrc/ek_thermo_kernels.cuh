@@ -80,9 +80,21 @@ constexpr unsigned kSmemBytes = 0;
 
 constexpr int kThreads = EK_MAX_THREADS;  // CTA size is a compile-time constant: tile offsets become immediates
 
-// Cold path of a lean build: recompute one point with the exact functor (libdevice math, IEEE division).
-// Out of line on purpose: its registers and code stay out of the hot loop.
-template <class OpE, typename T> __device__ __noinline__ void exact_point(const T* a, T* r, const Params P) {
+template <typename T> __device__ __forceinline__ bool is_nan_val(T v) { return v != v; }
+
+// Cold path of a lean build: a result of the fast functor contains a NaN.  Out of line on purpose (its registers and
+// code stay out of the hot loop).  Missing-value points -- every ARRAY input NaN (`array_mask` bit k = input k is an
+// array, not a broadcast scalar) -- keep the fast result: every output depends on an array input, so IEEE propagation
+// makes the exact result NaN as well (masked fields, e.g. below-ground points, therefore stay on the fast path).
+// Any other point is recomputed with the exact functor (libdevice math, IEEE division).
+template <class OpE, typename T> __device__ __noinline__ void cold_point(const T* a, T* r, const Params P, const uint32_t array_mask) {
+    bool missing = array_mask != 0;
+#pragma unroll
+    for (int k = 0; k < OpE::NIN; ++k)
+        if ((array_mask >> k) & 1u) missing = missing && is_nan_val(a[k]);
+    if (missing) return;
+#pragma unroll
+    for (int o = 0; o < OpE::NOUT; ++o) r[o] = T(0);
     OpE::template apply<T>(a, r, P);
 }
 
@@ -96,8 +108,9 @@ template <int NOUT> __device__ __forceinline__ bool any_nan(const double* r) {
 }
 template <int NOUT> __device__ __forceinline__ bool any_nan(const float*) { return false; }  // float32 lean math is self-contained
 
-// One grid point: fast functor, then (lean build, float64 only) the exact functor if the result has a NaN in it.
-template <class Op, class OpE, typename T> __device__ __forceinline__ void point(const T* a, T* r, const Params& P) {
+// One grid point: fast functor, then (lean build, float64 only) the cold path if the result has a NaN in it.
+template <class Op, class OpE, typename T>
+__device__ __forceinline__ void point(const T* a, T* r, const Params& P, const uint32_t array_mask) {
 #pragma unroll
     for (int o = 0; o < Op::NOUT; ++o) r[o] = T(0);
     Op::template apply<T>(a, r, P);
@@ -107,11 +120,13 @@ template <class Op, class OpE, typename T> __device__ __forceinline__ void point
 #pragma unroll
         for (int k = 0; k < Op::NIN; ++k) a2[k] = a[k];
 #pragma unroll
-        for (int o = 0; o < Op::NOUT; ++o) r2[o] = T(0);
-        exact_point<OpE, T>(a2, r2, P);
+        for (int o = 0; o < Op::NOUT; ++o) r2[o] = r[o];
+        cold_point<OpE, T>(a2, r2, P, array_mask);
 #pragma unroll
         for (int o = 0; o < Op::NOUT; ++o) r[o] = r2[o];
     }
+#else
+    (void)array_mask;
 #endif
 }
 
@@ -149,7 +164,7 @@ __device__ __forceinline__ void load_tile(TileRegs<Op, T, UNROLL>& r, const InAr
 
 template <class Op, class OpE, typename T, int UNROLL, bool VECOK>
 __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>& r, const OutArgs<Op::NOUT>& out, const int64_t base,
-                                                   const Params& P) {
+                                                   const Params& P, const uint32_t array_mask) {
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;
     constexpr int VEC = Vec16<T>::N;
@@ -162,7 +177,7 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
             T a[NIN], res[NOUT];
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
-            point<Op, OpE, T>(a, res, P);
+            point<Op, OpE, T>(a, res, P, array_mask);
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) y[o][v] = res[o];
         }
@@ -186,7 +201,8 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
 // tile are issued before the math of the current one, so every warp keeps HBM requests in flight while it
 // computes (two register sets, A and B, alternate; no dynamic register indexing).
 template <class Op, class OpE, typename T, int UNROLL, bool VECOK>
-__device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P) {
+__device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P,
+                                          const uint32_t array_mask) {
     constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
     const int64_t G = gridDim.x;
     const int64_t toff = (int64_t)threadIdx.x * Vec16<T>::N;
@@ -199,19 +215,19 @@ __device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutAr
         const int64_t tb = ta + G;
         const bool hb = tb < ntiles;
         if (hb) load_tile<Op, T, UNROLL, VECOK>(B, in, tb * TILE + toff);
-        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P, array_mask);
         if (!hb) break;
         ta = tb + G;
         const bool ha = ta < ntiles;
         if (ha) load_tile<Op, T, UNROLL, VECOK>(A, in, ta * TILE + toff);
-        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(B, out, tb * TILE + toff, P);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(B, out, tb * TILE + toff, P, array_mask);
         if (!ha) break;
     }
 #else
     for (; ta < ntiles; ta += G) {
         TileRegs<Op, T, UNROLL> A;
         load_tile<Op, T, UNROLL, VECOK>(A, in, ta * TILE + toff);
-        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P);
+        compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P, array_mask);
     }
 #endif
 }
@@ -227,17 +243,20 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS)
     if (sizeof(T) == 8) lean::init_tables();
 #endif
     const int64_t ntiles = n / TILE;
+    uint32_t array_mask = 0;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) array_mask |= (in.p[k] != nullptr) ? (1u << k) : 0u;
     if (vec_ok)
-        tile_loop<Op, OpE, T, UNROLL, true>(in, out, ntiles, P);
+        tile_loop<Op, OpE, T, UNROLL, true>(in, out, ntiles, P, array_mask);
     else
-        tile_loop<Op, OpE, T, UNROLL, false>(in, out, ntiles, P);
+        tile_loop<Op, OpE, T, UNROLL, false>(in, out, ntiles, P, array_mask);
 
     // tail: fewer than one tile of points, one point per thread, grid-stride
     for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         T a[NIN], r[NOUT];
 #pragma unroll
         for (int k = 0; k < NIN; ++k) a[k] = (in.p[k] != nullptr) ? __ldcs(static_cast<const T*>(in.p[k]) + i) : static_cast<T>(in.s[k]);
-        point<Op, OpE, T>(a, r, P);
+        point<Op, OpE, T>(a, r, P, array_mask);
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
             const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);

@@ -470,3 +470,32 @@ def test_cuda_graph_capture_and_replay(ek):
     tn = inp["t"] + 1.5
     np.testing.assert_allclose(out["theta"].cpu().numpy(), oracle.potential_temperature(tn, inp["p"]), rtol=1e-12)
     np.testing.assert_allclose(out["rh"].cpu().numpy(), oracle.relative_humidity_from_specific_humidity(tn, inp["q"], inp["p"]), rtol=1e-12)
+
+
+def test_missing_values_stay_nan_and_neighbours_stay_exact(ek):
+    """Masked fields: NaN in every input (a land/sea or below-ground mask), NaN in only one input, and NaN-free points
+    in the same warps.  Outputs must be NaN exactly where the oracle's are, and exact elsewhere."""
+    from ek_thermo import fused
+
+    n = 300_007
+    inp = random_inputs(n, seed=43)
+    t, q, p = (inp[k].copy() for k in ("t", "q", "p"))
+    rng = np.random.default_rng(43)
+    blk = (np.arange(n) // 5000) % 3 == 0  # contiguous masked blocks: all inputs missing
+    t[blk] = q[blk] = p[blk] = np.nan
+    only_q = rng.random(n) < 0.05  # scattered: one input missing
+    q[only_q] = np.nan
+    d = [torch.from_numpy(x).to(DEV) for x in (t, q, p)]
+    got = fused.suite_tqp(*d, outputs=tuple(fused.SUITE_TQP_OUTPUTS))
+    with np.errstate(all="ignore"):
+        want = oracle.suite_tqp(t, q, p)
+    for name in fused.SUITE_TQP_OUTPUTS:
+        g, w = got[name].cpu().numpy(), np.asarray(want[name])
+        np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg=name)
+        np.testing.assert_allclose(g, w, rtol=1e-12, atol=0, equal_nan=True, err_msg=name)
+    assert np.isnan(got["theta"].cpu().numpy()[blk]).all() and not np.isnan(got["tv"].cpu().numpy()[~blk & ~only_q]).any()
+    # scalar pressure with a masked t/q field
+    got = fused.suite_tqp(d[0], d[1], 85000.0, outputs=("theta", "rh", "td"))
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(got["theta"].cpu().numpy(), oracle.potential_temperature(t, 85000.0), rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(got["td"].cpu().numpy(), oracle.dewpoint_from_specific_humidity(q, 85000.0), rtol=1e-12, equal_nan=True)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ctas", default="16")
     ap.add_argument("--only", default="")
+    ap.add_argument("--masked", type=float, default=0.0, help="fraction of points (contiguous blocks) set to NaN in every input")
     ap.add_argument("--graph", action="store_true", help="also time the fused suites replayed from a CUDA graph")
     ap.add_argument("--realistic", action="store_true", help="IFS-like smooth t(p) instead of uniform random t")
     a = ap.parse_args()
@@ -43,6 +44,11 @@ def main():
     q = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
     td = t - torch.empty(n, device=dev, dtype=torch.float64).uniform_(0.0, 30.0, generator=g)
     r = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0, 100.0, generator=g)
+    if a.masked > 0:  # missing values in contiguous blocks of 64 Ki points
+        m = (torch.arange(n, device=dev) // 65536) % 100 < int(a.masked * 100)
+        for x in (t, p, q, td, r):
+            x[m] = float("nan")
+        del m
     t, p, q, td, r = (x.to(dt) for x in (t, p, q, td, r))
     out5 = {k: torch.empty_like(t) for k in ("theta", "es", "rh", "td", "tv", "q", "w", "e", "thetav")}
 
