@@ -27,6 +27,9 @@ using namespace ek;
 #ifndef EK_HYB_LU
 #define EK_HYB_LU 2
 #endif
+#ifndef EK_COL_LU
+#define EK_COL_LU 4  // the column (geopotential) kernel has little math per level: more levels in flight
+#endif
 
 namespace {
 
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) column_geopotential_ker
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
     constexpr int NARR = GIVEN_AD ? 4 : 2;
+    constexpr int CLU = GIVEN_AD ? 2 : EK_COL_LU;  // levels in flight per thread
 #if EK_LEAN_DEVICE
     if (sizeof(T) == 8) lean::init_tables();
 #endif
@@ -257,16 +261,16 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) column_geopotential_ker
 #pragma unroll
             for (int j = 0; j < VEC; ++j) hs[j] = EK_FAST_NS::geom_from_z(zs[j]);
         }
-        for (int k = g.nlev - 1; k >= 0; k -= 2) {
-            T x[2][NARR][VEC];
+        for (int k = g.nlev - 1; k >= 0; k -= CLU) {
+            T x[CLU][NARR][VEC];
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < CLU; ++u)
                 if (k - u >= 0) {
 #pragma unroll
                     for (int c = 0; c < NARR; ++c) ld_row<T, VECOK>(arr[c] + (int64_t)(k - u) * g.npl, i0, g.npl, x[u][c], true);
                 }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CLU; ++u) {
                 const int kk = k - u;
                 if (kk < 0) break;
                 T a0 = T(0), b0 = T(0), a1 = T(0), b1 = T(0);
