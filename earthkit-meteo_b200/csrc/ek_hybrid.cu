@@ -28,7 +28,8 @@ using namespace ek;
 #define EK_HYB_LU 2
 #endif
 #ifndef EK_COL_LU
-#define EK_COL_LU 4  // the column (geopotential) kernel has little math per level: more levels in flight
+#define EK_COL_LU 2  // levels in flight in the column (geopotential) kernel; measured 2 -> 4.46 ms, 4 -> 5.40 ms, 6 -> 7.68 ms
+                     // (O1280 x 137 fp64: beyond 2 the 64-register cap spills)
 #endif
 
 namespace {
