@@ -27,6 +27,9 @@ using namespace ek;
 #ifndef EK_HYB_LU
 #define EK_HYB_LU 2
 #endif
+#ifndef EK_HYB_PREFETCH
+#define EK_HYB_PREFETCH 0  // L2 prefetch of the next level pair: measured within the run-to-run noise (10.6-11.5 ms either way), off
+#endif
 #ifndef EK_COL_LU
 #define EK_COL_LU 2  // levels in flight in the column (geopotential) kernel; measured 2 -> 4.46 ms, 4 -> 5.40 ms, 6 -> 7.68 ms
                      // (O1280 x 137 fp64: beyond 2 the 64-register cap spills)
@@ -194,6 +197,14 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) suite_hybrid_kernel(con
 #pragma unroll
                     for (int c = 0; c < 2; ++c) ld_row<T, VECOK>(tq[c] + (int64_t)(k + u) * g.npl, i0, g.npl, x[u][c], true);
                 }
+#if EK_HYB_PREFETCH
+#pragma unroll
+            for (int u = 0; u < LU; ++u)  // ask L2 for the next pair of levels while this pair is being computed
+                if (k + LU + u < k1) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(tq[c] + (int64_t)(k + LU + u) * g.npl + i0));
+                }
+#endif
 #pragma unroll
             for (int u = 0; u < LU; ++u) {
                 if (k + u >= k1) break;
