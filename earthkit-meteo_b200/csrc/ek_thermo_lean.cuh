@@ -23,6 +23,10 @@
 #pragma once
 #include "ek_thermo_lean_tables.inc"
 
+#ifndef EK_LEAN_HORNER
+#define EK_LEAN_HORNER 0  // 1: Horner instead of Estrin in log_/exp_ (one fewer two-constant FMA each).  Measured: no change
+#endif                    // (suite 0.907 -> 0.902, ept+wbpt 0.755 -> 0.764 of the HBM roofline), so Estrin's shorter chain stays.
+
 namespace ek {
 namespace lean {
 
@@ -81,10 +85,17 @@ __device__ __forceinline__ double log_(double x) {
     const double r = fma(z, tc.x, -1.0);
     const double kd = (double)k;
     const double r2 = r * r;
+#if EK_LEAN_HORNER
+    double s = fma(r, kLog[4], kLog[3]);  // Horner: one FMA with two constant operands instead of two
+    s = fma(s, r, kLog[2]);
+    s = fma(s, r, kLog[1]);
+    s = fma(s, r, kLog[0]);
+#else
     double p = fma(r, kLog[4], kLog[3]);
     const double q = fma(r, kLog[2], kLog[1]);
     p = fma(r2, p, q);
     const double s = fma(r, p, kLog[0]);
+#endif
     const double t1 = fma(kd, kRed[3], tc.y);
     const double t2 = fma(kd, kRed[4], r);
     const double y = fma(r2, s, t2) + t1;
@@ -100,9 +111,15 @@ __device__ __forceinline__ double exp_(double x) {
     r = fma(kd, -kRed[2], r);
     const double T = lds_exp(ki & (EK_EXP_TAB_N - 1));
     const double r2 = r * r;
+#if EK_LEAN_HORNER
+    double s = fma(r, kExp[3], kExp[2]);
+    s = fma(s, r, kExp[1]);
+    s = fma(s, r, kExp[0]);
+#else
     const double a = fma(r, kExp[1], kExp[0]);
     const double b = fma(r, kExp[3], kExp[2]);
     const double s = fma(r2, b, a);
+#endif
     const double p = fma(r2, s, r);
     const double y = fma(T, p, T);
     return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
