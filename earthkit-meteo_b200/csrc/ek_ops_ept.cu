@@ -5,6 +5,29 @@
 
 using namespace ek;
 
+#if EK_LEAN_MATH
+// Fills lean::ek_bisect_tab: {es_mixed(t), ln t} for the 4095 nodes of the bisection tree (see ek_thermo_lean.cuh).
+// Launched on the caller's stream right before every bisection kernel: ~3 us, stateless, safe under graph capture.
+__global__ void bisect_tab_init_kernel() {
+#if EK_LEAN_DEVICE
+    lean::init_tables();
+    for (int node = 1 + blockIdx.x * blockDim.x + threadIdx.x; node < EK_BISECT_NODES; node += gridDim.x * blockDim.x) {
+        const double t = fastm::bisect_node_t(node);
+        lean::ek_bisect_tab[node] = make_double2(fastm::es_mixed(t), lean::log_(t));
+    }
+#endif
+}
+static int bisect_prepare(void* stream) {
+    bisect_tab_init_kernel<<<16, 256, kSmemBytes, static_cast<cudaStream_t>(stream)>>>();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error((int)err, "bisect table init failed: %s", cudaGetErrorString(err));
+    return EK_OK;
+}
+#else
+static int bisect_prepare(void*) { return EK_OK; }
+#endif
+
 template <typename T, int M, int TM>
 static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p0, void* ept_out, void* wb_out, int64_t n, void* stream) {
     ek_operand ins[3] = {t, h, p};
@@ -12,6 +35,10 @@ static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p
     Params P;
     P.opt0 = hum;
     P.opt1 = at_p0;
+    if (TM == TM_BISECT && sizeof(T) == 8 && n > 0) {
+        const int rc = bisect_prepare(stream);
+        if (rc != EK_OK) return rc;
+    }
     return launch<EK_OPS(OpEptWb<M, TM>), T>("ept_wet_bulb", ins, outs, n, P, stream);
 }
 
@@ -84,7 +111,13 @@ EK_API(saturation_ept, (ek_operand t, ek_operand p, int m, void* out, int64_t n,
 
 // ---- temperature on a moist adiabat (T:1472-1509) ---------------------------------------------------
 template <typename T, int M> static int t_on_ma_m(int tm, const ek_operand* ins, void* const* outs, int64_t n, void* stream) {
-    if (tm == EK_TM_BISECT) return launch<EK_OPS(OpTOnMa<M, TM_BISECT>), T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
+    if (tm == EK_TM_BISECT) {
+        if (sizeof(T) == 8 && n > 0) {
+            const int rc = bisect_prepare(stream);
+            if (rc != EK_OK) return rc;
+        }
+        return launch<EK_OPS(OpTOnMa<M, TM_BISECT>), T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
+    }
     if (tm == EK_TM_NEWTON) return launch<EK_OPS(OpTOnMa<M, TM_NEWTON>), T>("temperature_on_moist_adiabat", ins, outs, n, Params{}, stream);
     return set_error(EK_ERR_ENUM, "temperature_on_moist_adiabat: invalid t_method id %d", tm);
 }

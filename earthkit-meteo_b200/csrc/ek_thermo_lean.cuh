@@ -135,6 +135,14 @@ __device__ __forceinline__ double pow_t0_over_(double x, double y) { return exp_
 __device__ __forceinline__ double kappa_log_p0_over(double x) { return ::ek::kCdev.kappa * (kRed[6] - log_(x)); }
 __device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek::kC.kappa * ((float)EK_LOG_P0 - __logf(x)); }
 
+// ---- bisection tree table (see t_on_ma_bisect_tab in ek_thermo_formulas.inc) -----------------------------------
+// The reference's moist-adiabat bisection (T:1055-1079) starts every point at T0 - 20 and moves by +-60, +-30, ... K:
+// after i steps the iterate is one of 2^i values that do not depend on the data.  {es_mixed(t), ln t} of the 4095
+// nodes visited by the 12 steps are tabulated once per launch (bisect_tab_init_kernel), which removes the exponential,
+// the phase blend and two reciprocals from every iteration.  Heap numbering: root = 1, children 2n (down), 2n + 1 (up).
+#define EK_BISECT_NODES 4096
+static __device__ double2 ek_bisect_tab[EK_BISECT_NODES];
+
 // ---- float32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
 // MUFU.LG2-based: absolute error ~1e-6 on |ln x| <= 12 -- after the factors it meets on this path (kappa = 0.29 in the
