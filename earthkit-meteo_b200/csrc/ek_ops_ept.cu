@@ -12,8 +12,10 @@ __global__ void bisect_tab_init_kernel() {
 #if EK_LEAN_DEVICE
     lean::init_tables();
     for (int node = 1 + blockIdx.x * blockDim.x + threadIdx.x; node < EK_BISECT_NODES; node += gridDim.x * blockDim.x) {
-        const double t = fastm::bisect_node_t(node);
+        const double t = fastm::bisect_node_t<double>(node);
         lean::ek_bisect_tab[node] = make_double2(fastm::es_mixed(t), lean::log_(t));
+        const float tf = fastm::bisect_node_t<float>(node);
+        lean::ek_bisect_tab_f[node] = make_float2(fastm::es_mixed(tf), lean::log_(tf));
     }
 #endif
 }
@@ -35,7 +37,7 @@ static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p
     Params P;
     P.opt0 = hum;
     P.opt1 = at_p0;
-    if (TM == TM_BISECT && sizeof(T) == 8 && n > 0) {
+    if (TM == TM_BISECT && n > 0) {
         const int rc = bisect_prepare(stream);
         if (rc != EK_OK) return rc;
     }
@@ -112,7 +114,7 @@ EK_API(saturation_ept, (ek_operand t, ek_operand p, int m, void* out, int64_t n,
 // ---- temperature on a moist adiabat (T:1472-1509) ---------------------------------------------------
 template <typename T, int M> static int t_on_ma_m(int tm, const ek_operand* ins, void* const* outs, int64_t n, void* stream) {
     if (tm == EK_TM_BISECT) {
-        if (sizeof(T) == 8 && n > 0) {
+        if (n > 0) {
             const int rc = bisect_prepare(stream);
             if (rc != EK_OK) return rc;
         }

@@ -106,16 +106,32 @@ template <int NOUT> __device__ __forceinline__ bool any_nan(const double* r) {
     for (int o = 0; o < NOUT; ++o) m = max(m, __double2hiint(r[o]) & 0x7fffffff);
     return m >= 0x7ff80000;
 }
-template <int NOUT> __device__ __forceinline__ bool any_nan(const float*) { return false; }  // float32 lean math is self-contained
+template <int NOUT> __device__ __forceinline__ bool any_nan(const float* r) {
+    int m = 0;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) m = max(m, __float_as_int(r[o]) & 0x7fffffff);
+    return m > 0x7f800000;
+}
 
-// One grid point: fast functor, then (lean build, float64 only) the cold path if the result has a NaN in it.
+// float32 lean math is self-contained (its primitives follow IEEE special values), so float32 points skip the cold
+// path -- except for functors that declare `COLD_F32 = true`: the tabulated bisection poisons ties, underflow and
+// non-positive inputs with NaN in float32 as well.
+template <class Op, class = void> struct ColdF32 {
+    static constexpr bool value = false;
+};
+template <class Op> struct ColdF32<Op, decltype((void)Op::COLD_F32)> {
+    static constexpr bool value = Op::COLD_F32;
+};
+
+// One grid point: fast functor, then (lean build; float64, or float32 where the functor asks) the cold path if the
+// result has a NaN in it.
 template <class Op, class OpE, typename T>
 __device__ __forceinline__ void point(const T* a, T* r, const Params& P, const uint32_t array_mask) {
 #pragma unroll
     for (int o = 0; o < Op::NOUT; ++o) r[o] = T(0);
     Op::template apply<T>(a, r, P);
 #if EK_LEAN_DEVICE
-    if (sizeof(T) == 8 && __builtin_expect(any_nan<Op::NOUT>(r), 0)) {
+    if ((sizeof(T) == 8 || ColdF32<Op>::value) && __builtin_expect(any_nan<Op::NOUT>(r), 0)) {
         T a2[Op::NIN], r2[Op::NOUT];
 #pragma unroll
         for (int k = 0; k < Op::NIN; ++k) a2[k] = a[k];

@@ -131,9 +131,15 @@ __device__ __forceinline__ double pow_p0_over_(double x, double y) { return exp_
 __device__ __forceinline__ double pow_over_p0_(double x, double y) { return exp_(y * (log_(x) - kRed[6])); }
 __device__ __forceinline__ double pow_t0_over_(double x, double y) { return exp_(y * (kRed[7] - log_(x))); }
 
+// ln(p0 / x) without the division
+__device__ __forceinline__ double log_p0_over(double x);
+__device__ __forceinline__ float log_p0_over(float x) { return (float)EK_LOG_P0 - __logf(x); }
+
 // kappa * ln(p0 / x): the exponent of the Exner factor, for callers that fold it into a larger exponential
 __device__ __forceinline__ double kappa_log_p0_over(double x) { return ::ek::kCdev.kappa * (kRed[6] - log_(x)); }
 __device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek::kC.kappa * ((float)EK_LOG_P0 - __logf(x)); }
+
+__device__ __forceinline__ double log_p0_over(double x) { return kRed[6] - log_(x); }
 
 // ---- bisection tree table (see t_on_ma_bisect_tab in ek_thermo_formulas.inc) -----------------------------------
 // The reference's moist-adiabat bisection (T:1055-1079) starts every point at T0 - 20 and moves by +-60, +-30, ... K:
@@ -142,6 +148,7 @@ __device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek
 // the phase blend and two reciprocals from every iteration.  Heap numbering: root = 1, children 2n (down), 2n + 1 (up).
 #define EK_BISECT_NODES 4096
 static __device__ double2 ek_bisect_tab[EK_BISECT_NODES];
+static __device__ float2 ek_bisect_tab_f[EK_BISECT_NODES];  // float32 twin: nodes, es and ln t in float32 arithmetic
 
 // ---- float32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
