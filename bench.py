@@ -332,6 +332,7 @@ def run_ours(args, kind, outputs, levels, npl, dtype):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_cpus = hostpipe.bind_host_to_device(device) if world > 1 else None  # pinned e2e buffers next to the rank's GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -415,6 +416,7 @@ def run_ours(args, kind, outputs, levels, npl, dtype):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": args.workload, "outputs": list(outputs), "levels": levels, "points_per_level": npl,
                        "points_per_gpu": n, "bytes_per_point": bytes_per_pt, "parallelism": f"shard x{world} (no collective)",
+                       "host_cpus_rank0": (f"{len(numa_cpus)} CPUs local to the GPU" if numa_cpus else "unbound"),
                        "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (bytes_per_pt * n / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.workload), "peak_source": peak_src,

@@ -359,9 +359,9 @@ static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhal
     if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
     const bool vec = npl % Vec16<T>::N == 0 && ok16(sp) && ok16(full) && ok16(half) && ok16(delta) && ok16(alpha);
     if (vec)
-        hybrid_pressure_kernel<T, true><<<blocks, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+        launch_kernel<&hybrid_pressure_kernel<T, true>, T>(blocks, static_cast<cudaStream_t>(stream), g);
     else
-        hybrid_pressure_kernel<T, false><<<blocks, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+        launch_kernel<&hybrid_pressure_kernel<T, false>, T>(blocks, static_cast<cudaStream_t>(stream), g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
@@ -404,11 +404,11 @@ static int impl_geopotential_on_hybrid_levels(const void* t, const void* q, int 
     const bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(alpha) && ok16(delta) && ok16(zs) && ok16(out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (given) {
-        if (vec) column_geopotential_kernel<T, true, true><<<blocks, kThreads, kSmemBytes, st>>>(g);
-        else column_geopotential_kernel<T, true, false><<<blocks, kThreads, kSmemBytes, st>>>(g);
+        if (vec) launch_kernel<&column_geopotential_kernel<T, true, true>, T>(blocks, st, g);
+        else launch_kernel<&column_geopotential_kernel<T, true, false>, T>(blocks, st, g);
     } else {
-        if (vec) column_geopotential_kernel<T, false, true><<<blocks, kThreads, kSmemBytes, st>>>(g);
-        else column_geopotential_kernel<T, false, false><<<blocks, kThreads, kSmemBytes, st>>>(g);
+        if (vec) launch_kernel<&column_geopotential_kernel<T, false, true>, T>(blocks, st, g);
+        else launch_kernel<&column_geopotential_kernel<T, false, false>, T>(blocks, st, g);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
@@ -446,9 +446,9 @@ static int suite_hybrid(const void* t, const void* q, const void* sp, const void
 #define EK_LAUNCH_SH(M)                                                                          \
     do {                                                                                         \
         if (vec)                                                                                 \
-            suite_hybrid_kernel<OpM<M>, OpME<M>, T, true><<<blocks, kThreads, kSmemBytes, st>>>(g, P);  \
+            launch_kernel<&suite_hybrid_kernel<OpM<M>, OpME<M>, T, true>, T>(blocks, st, g, P);  \
         else                                                                                     \
-            suite_hybrid_kernel<OpM<M>, OpME<M>, T, false><<<blocks, kThreads, kSmemBytes, st>>>(g, P); \
+            launch_kernel<&suite_hybrid_kernel<OpM<M>, OpME<M>, T, false>, T>(blocks, st, g, P); \
     } while (0)
     if (out_mask == 0x1F)
         EK_LAUNCH_SH(0x1F);

@@ -19,6 +19,33 @@ extern std::atomic<uint64_t> g_launches;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Dynamic shared memory of a launch: the lean float64 tables; float32 kernels use none.
+template <typename T> constexpr unsigned smem_for() { return sizeof(T) == 8 ? kSmemBytes : 0u; }
+
+// Once per kernel instantiation and device: ask for a shared-memory carve-out that holds EK_MIN_CTAS CTAs' tables, so the
+// tables never lower the occupancy the register budget was chosen for (the driver's default carve-out heuristic may
+// pick a smaller one).  `Kernel` is the address of the __global__ instantiation.
+template <auto Kernel> inline void prepare_smem(unsigned smem_bytes) {
+    if (smem_bytes == 0) return;
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return;
+    const uint64_t bit = dev < 64 ? (1ull << dev) : 0;
+    if (bit && (done.load(std::memory_order_relaxed) & bit)) return;
+    const unsigned want = EK_MIN_CTAS * (smem_bytes + 1024u);  // + the per-CTA reservation
+    int pct = (int)((want * 100u + 228u * 1024u - 1u) / (228u * 1024u));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (smem_bytes > 48u * 1024u) cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (bit) done.fetch_or(bit, std::memory_order_relaxed);
+}
+
+// prepare_smem + launch of a kernel with the standard CTA size and the dtype's dynamic shared memory
+template <auto Kernel, typename T, typename... Args> inline void launch_kernel(int blocks, cudaStream_t st, Args... args) {
+    prepare_smem<Kernel>(smem_for<T>());
+    Kernel<<<blocks, kThreads, smem_for<T>(), st>>>(args...);
+}
+
 // Launch Op over n points.  ins[k].ptr == NULL means broadcast scalar ins[k].value; outs[o] == NULL means
 // "output o not wanted" (P.out_mask must agree).
 template <class Op, class OpE, typename T>
@@ -61,7 +88,8 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
 
-    ew_kernel<Op, OpE, T, EK_UNROLL><<<(unsigned)blocks, threads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
+    prepare_smem<&ew_kernel<Op, OpE, T, EK_UNROLL>>(smem_for<T>());
+    ew_kernel<Op, OpE, T, EK_UNROLL><<<(unsigned)blocks, threads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));

@@ -8,7 +8,7 @@
 //   * all intermediates of a point live in registers; outputs are stored as soon as a vector is done;
 //   * tiles are handed to CTAs round-robin (grid-stride), grid sized as SMs x CTAs-per-SM;
 //   * no shared-memory staging, no TMA, no tensor cores: there is nothing to stage or contract (shared memory only
-//     holds the 2.5 KB log/exp tables of the lean math, ek_thermo_lean.cuh);
+//     holds the log/exp tables of the lean math, ek_thermo_lean.cuh);
 //   * every point goes through the fast (lean-math) functor; a point whose result contains a NaN is recomputed by
 //     the exact functor in an out-of-line cold path, so special values behave exactly as the reference.
 // Broadcast scalars arrive by value (never materialised); unaligned views use scalar ld/st inside the
@@ -73,7 +73,7 @@ template <> struct Vec16<float> {
 
 // dynamic shared memory a launch must provide (the lean fp64 log/exp tables)
 #if EK_LEAN_MATH
-constexpr unsigned kSmemBytes = 2 * 8 * 128 + 8 * 64;  // lean::Tables (checked against sizeof in the kernel)
+constexpr unsigned kSmemBytes = 2 * 8 * EK_LOG_TAB_N + 8 * EK_EXP_TAB_N;  // lean::Tables (checked against sizeof in the kernel)
 #else
 constexpr unsigned kSmemBytes = 0;
 #endif

@@ -8,8 +8,11 @@
 // need (correct rounding of the quotient, denormal results):
 //
 //   rcp_/div_  MUFU.RCP64H seed (2^-19.9, measured: tools/probe_mufu.cu) + one cubic Newton step: <= 2 ulp
-//   log_       128-entry {1/c, ln c} table, r = z/c - 1 (|r| < 2^-8), degree-6 log1p polynomial: ~1 ulp (abs 2e-16)
-//   exp_       64-entry 2^(j/64) table, degree-5 polynomial on |r| <= ln2/128: ~1 ulp
+//   log_       2^L-entry {1/c, ln c} table, r = z/c - 1 (|r| < 2^-(L+1)), log1p polynomial of degree 4 (L >= 10),
+//              5 (L >= 8) or 6: ~1 ulp (abs 2e-16)
+//   exp_       2^E-entry 2^(j/2^E) table, polynomial of degree 3 (E >= 11), 4 (E >= 8) or 5 on |r| <= ln2/2^(E+1): ~1 ulp
+//   (L = EK_LOG_TAB_BITS, E = EK_EXP_TAB_BITS, set by tools/gen_lean_tables.py; the shipped tables are L = 10, E = 11:
+//   32 KB of shared memory per CTA buy two FP64 instructions per log_ and per exp_)
 //   pow_       exp_(y * log_(x)): relative error ~ |y ln x| * 2e-16
 //
 // The fp64 primitives are branch-free.  Outside their fast domain (x <= 0, denormal, inf, NaN for log_; |x| >= 708
@@ -23,22 +26,37 @@
 #pragma once
 #include "ek_thermo_lean_tables.inc"
 
-#ifndef EK_LEAN_HORNER
-#define EK_LEAN_HORNER 0  // 1: Horner instead of Estrin in log_/exp_ (one fewer two-constant FMA each).  Measured: no change
-#endif                    // (suite 0.907 -> 0.902, ept+wbpt 0.755 -> 0.764 of the HBM roofline), so Estrin's shorter chain stays.
+#if EK_LOG_TAB_BITS >= 10
+#define EK_LOG_DEG 4
+#elif EK_LOG_TAB_BITS >= 8
+#define EK_LOG_DEG 5
+#else
+#define EK_LOG_DEG 6
+#endif
+#if EK_EXP_TAB_BITS >= 11
+#define EK_EXP_DEG 3
+#elif EK_EXP_TAB_BITS >= 8
+#define EK_EXP_DEG 4
+#else
+#define EK_EXP_DEG 5
+#endif
+#ifndef EK_LEAN_LOG_HILO
+#define EK_LEAN_LOG_HILO 1  // 1: k*ln2 added as a hi/lo pair (abs error of log_ ~2e-16); 0: one FMA less, ~1.5 ulp of the result
+#endif
 
 namespace ek {
 namespace lean {
 
 struct Tables {
     double2 log_tab[EK_LOG_TAB_N];  // {invc, logc}
-    double exp_tab[EK_EXP_TAB_N];   // 2^(j/64)
+    double exp_tab[EK_EXP_TAB_N];   // 2^(j/N)
 };
 
 // polynomial coefficients: constant bank -> uniform registers, never immediates
 __constant__ double kLog[5] = {-0.5, 0x1.5555555555555p-2 /*1/3*/, -0.25, 0x1.999999999999ap-3 /*1/5*/, -0x1.5555555555555p-3 /*-1/6*/};
 __constant__ double kExp[4] = {0.5, 0x1.5555555555555p-3 /*1/6*/, 0x1.5555555555555p-5 /*1/24*/, 0x1.1111111111111p-7 /*1/120*/};
-__constant__ double kRed[8] = {EK_INVLN2_N, EK_LN2N_HI, EK_LN2N_LO, EK_LN2_HI, EK_LN2_LO, 0x1.8p52 /*magic*/, EK_LOG_P0, EK_LOG_T0DJ};
+__constant__ double kRed[9] = {EK_INVLN2_N, EK_LN2N_HI, EK_LN2N_LO, EK_LN2_HI,   EK_LN2_LO, 0x1.8p52 /*magic*/,
+                               EK_LOG_P0,   EK_LOG_T0DJ, 0x1.62e42fefa39efp-1 /*ln 2*/};
 
 __device__ __forceinline__ Tables* tables() {
     extern __shared__ __align__(16) unsigned char ek_smem_raw[];
@@ -59,9 +77,12 @@ __device__ __forceinline__ double lds_exp(int j) {
 }
 
 __device__ __forceinline__ void init_tables() {
-    Tables* t = tables();
-    for (int i = threadIdx.x; i < EK_LOG_TAB_N; i += blockDim.x) t->log_tab[i] = make_double2(ek_log_tab_g[2 * i], ek_log_tab_g[2 * i + 1]);
-    for (int i = threadIdx.x; i < EK_EXP_TAB_N; i += blockDim.x) t->exp_tab[i] = ek_exp_tab_g[i];
+    // 16-byte copies global (L2-resident after the first CTA) -> shared
+    double2* dst = reinterpret_cast<double2*>(tables());
+    const double2* lg = reinterpret_cast<const double2*>(ek_log_tab_g);
+    const double2* ex = reinterpret_cast<const double2*>(ek_exp_tab_g);
+    for (int i = threadIdx.x; i < EK_LOG_TAB_N; i += blockDim.x) dst[i] = __ldg(lg + i);
+    for (int i = threadIdx.x; i < EK_EXP_TAB_N / 2; i += blockDim.x) dst[EK_LOG_TAB_N + i] = __ldg(ex + i);
     __syncthreads();
 }
 
@@ -78,27 +99,31 @@ __device__ __forceinline__ double log_(double x) {
     const int hi = __double2hiint(x);
     const bool bad = (unsigned)(hi - 0x00100000) >= 0x7fe00000u;  // <= 0, denormal, inf, NaN: answer NaN
     const int tmp = hi - 0x3fe60000;
-    const int i = (tmp >> 13) & (EK_LOG_TAB_N - 1);
+    const int i = (tmp >> (20 - EK_LOG_TAB_BITS)) & (EK_LOG_TAB_N - 1);
     const int k = tmp >> 20;
     const double z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
     const double2 tc = lds_log(i);
     const double r = fma(z, tc.x, -1.0);
     const double kd = (double)k;
     const double r2 = r * r;
-#if EK_LEAN_HORNER
-    double s = fma(r, kLog[4], kLog[3]);  // Horner: one FMA with two constant operands instead of two
-    s = fma(s, r, kLog[2]);
-    s = fma(s, r, kLog[1]);
-    s = fma(s, r, kLog[0]);
-#else
+    // log1p(r) = r + r^2 s(r), s = -1/2 + r/3 - r^2/4 + ... (Estrin: short dependency chains)
+#if EK_LOG_DEG == 6
     double p = fma(r, kLog[4], kLog[3]);
     const double q = fma(r, kLog[2], kLog[1]);
     p = fma(r2, p, q);
     const double s = fma(r, p, kLog[0]);
+#elif EK_LOG_DEG == 5
+    const double s = fma(r2, fma(r, kLog[3], kLog[2]), fma(r, kLog[1], kLog[0]));
+#else
+    const double s = fma(r2, kLog[2], fma(r, kLog[1], kLog[0]));
 #endif
+#if EK_LEAN_LOG_HILO
     const double t1 = fma(kd, kRed[3], tc.y);
     const double t2 = fma(kd, kRed[4], r);
     const double y = fma(r2, s, t2) + t1;
+#else
+    const double y = fma(r2, s, r) + fma(kd, kRed[8], tc.y);
+#endif
     return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y), __double2loint(y));
 }
 
@@ -111,18 +136,17 @@ __device__ __forceinline__ double exp_(double x) {
     r = fma(kd, -kRed[2], r);
     const double T = lds_exp(ki & (EK_EXP_TAB_N - 1));
     const double r2 = r * r;
-#if EK_LEAN_HORNER
-    double s = fma(r, kExp[3], kExp[2]);
-    s = fma(s, r, kExp[1]);
-    s = fma(s, r, kExp[0]);
+    // e^r - 1 = r + r^2 s(r), s = 1/2 + r/6 + r^2/24 + r^3/120
+#if EK_EXP_DEG == 5
+    const double s = fma(r2, fma(r, kExp[3], kExp[2]), fma(r, kExp[1], kExp[0]));
+#elif EK_EXP_DEG == 4
+    const double s = fma(r2, kExp[2], fma(r, kExp[1], kExp[0]));
 #else
-    const double a = fma(r, kExp[1], kExp[0]);
-    const double b = fma(r, kExp[3], kExp[2]);
-    const double s = fma(r2, b, a);
+    const double s = fma(r, kExp[1], kExp[0]);
 #endif
     const double p = fma(r2, s, r);
     const double y = fma(T, p, T);
-    return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
+    return __hiloint2double(bad ? 0x7ff80000 : __double2hiint(y) + ((ki >> EK_EXP_TAB_BITS) << 20), __double2loint(y));
 }
 
 __device__ __forceinline__ double pow_(double x, double y) { return exp_(y * log_(x)); }

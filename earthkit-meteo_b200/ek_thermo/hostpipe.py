@@ -21,6 +21,41 @@ def pinned_empty(n, dtype=np.float64):
     return t.numpy()
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device="cuda:0"):
+    """Restrict the calling process to the CPUs next to `device` (its PCIe root's NUMA node).
+
+    Page-locked buffers allocated afterwards land in that node's memory (Linux allocates on the node of the
+    allocating thread), so H2D / D2H copies do not cross the socket interconnect.  Matters when one process per GPU
+    streams host fields through several GPUs of a multi-socket box at once.  Returns the CPU set it bound to, or
+    None when the topology cannot be read (no sysfs entry, no overlap with the allowed CPUs) -- never raises.
+    """
+    import os
+
+    try:
+        pr = torch.cuda.get_device_properties(torch.device(device))
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            local = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return sorted(cpus) or None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):
+        return None
+
+
 class HostSuite:
     """Reusable pipeline: owns the device workspace (allocated once through torch) and the stream slots."""
 

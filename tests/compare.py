@@ -8,12 +8,25 @@ tie: such points are counted and bounded, all others must agr
 import numpy as np
 
 
+def _step_ulps(a, k):
+    """`a` moved by k ulps of its dtype (k may be negative)."""
+    out = a
+    target = np.asarray(np.inf if k > 0 else -np.inf, dtype=a.dtype)
+    for _ in range(abs(k)):
+        out = np.nextafter(out, target)
+    return out
+
+
 def conditioning(case, args_np, k_out=0):
-    """Relative change of the oracle output when each input moves by one ulp of its dtype (max over inputs).
+    """Relative change of the oracle output per ulp of input perturbation (max over inputs).
 
     A result that differs from the oracle by no more than a 1-ulp input perturbation does is as exact as the
     formula allows: e.g. theta(t, p - es) loses digits without bound as p - es -> 0, for ANY two correctly
-    rounded exp implementations.  compare() accepts max(rtol, 4 x this) per point."""
+    rounded exp implementations.  compare() accepts max(rtol, 4 x this) per point.
+
+    Each input is moved by +-1 ulp and by +-16 ulps (change divided by 16): a single 1-ulp step can be absorbed by the
+    rounding of an intermediate (e.g. ept inside the "direct" wet-bulb fit, whose exponential amplifies one ulp of ept
+    to 1e-12 at unphysical edge points) and would then report a conditioning of zero."""
     import thermo_oracle as oracle
 
     fn = getattr(oracle, case.fn)
@@ -22,12 +35,13 @@ def conditioning(case, args_np, k_out=0):
         base = np.asarray(base[k_out] if isinstance(base, tuple) else base).astype(np.float64)
         cond = np.zeros(base.shape)
         for i, a in enumerate(args_np):
-            pert = list(args_np)
-            pert[i] = np.nextafter(a, np.asarray(np.inf, dtype=a.dtype))
-            r = fn(*pert, **case.kwargs)
-            r = np.asarray(r[k_out] if isinstance(r, tuple) else r).astype(np.float64)
-            d = np.abs(r - base) / np.maximum(np.abs(base), 1e-300)
-            cond = np.fmax(cond, np.where(np.isfinite(d), d, 0.0))
+            for k in (1, -1, 16, -16):
+                pert = list(args_np)
+                pert[i] = _step_ulps(a, k)
+                r = fn(*pert, **case.kwargs)
+                r = np.asarray(r[k_out] if isinstance(r, tuple) else r).astype(np.float64)
+                d = np.abs(r - base) / np.maximum(np.abs(base), 1e-300) / abs(k)
+                cond = np.fmax(cond, np.where(np.isfinite(d), d, 0.0))
     return cond
 
 

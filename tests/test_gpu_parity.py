@@ -522,3 +522,37 @@ def test_tabulated_bisection_reproduces_the_reference_iterates(ek, ept_method):
         np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
         differing = int(np.sum(np.abs(got - want) > 0))
         assert differing <= 2, f"{fn}/{ept_method}: {differing} of {n} points differ"
+
+
+def test_lean_math_accuracy_in_ulps(ek):
+    """The lean float64 primitives (table log/exp, Newton reciprocal) through the entry points that isolate them, on 2 M
+    physical points against the oracle (numpy libm): the error stays at the few-ulp level, four orders of magnitude
+    inside the 1e-12 parity bar.  The measured maxima are written to gpurun_out/lean_accuracy.json when that exists."""
+    import json
+    import os
+
+    n = 1 << 21
+    rng = np.random.default_rng(77)
+    t = rng.uniform(190.0, 320.0, n)
+    p = np.exp(rng.uniform(np.log(1.0), np.log(1.08e5), n))  # 1 Pa .. 1080 hPa, log-uniform: every exponent of log_
+    q = rng.uniform(1e-7, 0.03, n)
+    dev = {k: torch.from_numpy(v).to(DEV) for k, v in (("t", t), ("p", p), ("q", q))}
+    th = ek.thermo
+    pairs = {
+        "theta (log, exp)": (th.potential_temperature(dev["t"], dev["p"]), oracle.potential_temperature(t, p)),
+        "es water (rcp, exp)": (th.saturation_vapour_pressure(dev["t"], phase="water"), oracle.saturation_vapour_pressure(t, phase="water")),
+        "es mixed": (th.saturation_vapour_pressure(dev["t"]), oracle.saturation_vapour_pressure(t)),
+        "td from q (rcp, log, rcp)": (th.dewpoint_from_specific_humidity(dev["q"], dev["p"]), oracle.dewpoint_from_specific_humidity(q, p)),
+        "e from q (rcp)": (th.vapour_pressure_from_specific_humidity(dev["q"], dev["p"]), oracle.vapour_pressure_from_specific_humidity(q, p)),
+    }
+    ulps = {}
+    for name, (got, want) in pairs.items():
+        g = got.cpu().numpy()
+        ulps[name] = float(np.max(np.abs(g - want) / np.abs(want)) / 2.0**-52)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "lean_accuracy.json"), "w") as f:
+            json.dump({"lib": os.path.basename(ek._backend.LIB_PATH), "max_rel_err_in_2^-52": ulps}, f, indent=1)
+    # theta's exponent kappa*ln(p0/p) reaches 3.3, so an absolute error of 1 ulp(ln p) shows up as a few ulp of theta
+    assert ulps["theta (log, exp)"] < 32 and ulps["td from q (rcp, log, rcp)"] < 32, ulps
+    assert ulps["es water (rcp, exp)"] < 64 and ulps["es mixed"] < 64 and ulps["e from q (rcp)"] < 8, ulps

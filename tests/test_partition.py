@@ -89,3 +89,17 @@ def test_world_size_2_gloo():
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_host_binding_helper_without_a_gpu():
+    """CPU-list parsing, and the NUMA binding is a no-op (None, no exception) when there is no device to ask."""
+    import torch
+
+    from ek_thermo import hostpipe
+
+    assert hostpipe._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostpipe._parse_cpulist("") == set()
+    if not torch.cuda.is_available():
+        before = os.sched_getaffinity(0)
+        assert hostpipe.bind_host_to_device("cuda:0") is None
+        assert os.sched_getaffinity(0) == before

@@ -23,7 +23,7 @@ from ek_thermo import fused, thermo  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=6599680 * 24)
-    ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ctas", default="16")
     ap.add_argument("--only", default="")
