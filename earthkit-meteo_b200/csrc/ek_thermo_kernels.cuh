@@ -146,6 +146,43 @@ __device__ __forceinline__ void point(const T* a, T* r, const Params& P, const u
 #endif
 }
 
+// Functors that declare `BATCH = true` provide apply_n(): the N points of one 16-byte vector evaluated together (the
+// bisection advances them side by side).  Same per-point results and the same NaN -> cold-path rule as point().
+template <class Op, class = void> struct IsBatch {
+    static constexpr bool value = false;
+};
+template <class Op> struct IsBatch<Op, decltype((void)Op::BATCH)> {
+    static constexpr bool value = Op::BATCH;
+};
+
+template <class Op, class OpE, typename T, int N>
+__device__ __forceinline__ void points_n(const T (&a)[N][Op::NIN], T (&r)[N][Op::NOUT], const Params& P, const uint32_t array_mask) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int o = 0; o < Op::NOUT; ++o) r[j][o] = T(0);
+    Op::template apply_n<T, N>(a, r, P);
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8 || ColdF32<Op>::value) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (__builtin_expect(any_nan<Op::NOUT>(r[j]), 0)) {
+                T a2[Op::NIN], r2[Op::NOUT];
+#pragma unroll
+                for (int k = 0; k < Op::NIN; ++k) a2[k] = a[j][k];
+#pragma unroll
+                for (int o = 0; o < Op::NOUT; ++o) r2[o] = r[j][o];
+                cold_point<OpE, T>(a2, r2, P, array_mask);
+#pragma unroll
+                for (int o = 0; o < Op::NOUT; ++o) r[j][o] = r2[o];
+            }
+        }
+    }
+#else
+    (void)array_mask;
+#endif
+}
+
 // The inputs of one tile, per thread: UNROLL 16-byte vectors of every input array, in registers.
 template <class Op, typename T, int UNROLL> struct TileRegs {
     T x[Op::NIN][UNROLL][Vec16<T>::N];
@@ -207,14 +244,27 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         T y[NOUT][VEC];
+        if constexpr (IsBatch<Op>::value) {
+            T a[VEC][NIN], res[VEC][NOUT];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            T a[NIN], res[NOUT];
+            for (int v = 0; v < VEC; ++v)
 #pragma unroll
-            for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
-            point<Op, OpE, T>(a, res, P, array_mask);
+                for (int k = 0; k < NIN; ++k) a[v][k] = r.x[k][u][v];
+            points_n<Op, OpE, T, VEC>(a, res, P, array_mask);
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o) y[o][v] = res[o];
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) y[o][v] = res[v][o];
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                T a[NIN], res[NOUT];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
+                point<Op, OpE, T>(a, res, P, array_mask);
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) y[o][v] = res[o];
+            }
         }
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {

@@ -94,6 +94,23 @@ __device__ __forceinline__ double rcp_(double b) {
     return fma(fma(e, e, e), r0, r0);  // b = 0, denormal, inf, NaN: e is NaN -> NaN (the point is recomputed exactly)
 }
 __device__ __forceinline__ double div_(double a, double b) { return a * rcp_(b); }
+// Loop-invariant values the compiler would rather recompute inside a loop than keep live (it rematerialises cheap
+// expressions under register pressure): an empty asm makes the value opaque, so it is computed once.
+__device__ __forceinline__ double keep_in_register(double x) {
+    asm volatile("" : "+d"(x));
+    return x;
+}
+__device__ __forceinline__ float keep_in_register(float x) {
+    asm volatile("" : "+f"(x));
+    return x;
+}
+// 1/b to 2^-39 (seed + one quadratic step): for callers that only need the sign of a difference and treat a
+// near-tie as "recompute exactly" (the tabulated bisection)
+__device__ __forceinline__ double rcp_sign_(double b) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+    return fma(r0, fma(-b, r0, 1.0), r0);
+}
 
 __device__ __forceinline__ double log_(double x) {
     const int hi = __double2hiint(x);
@@ -176,6 +193,7 @@ static __device__ float2 ek_bisect_tab_f[EK_BISECT_NODES];  // float32 twin: nod
 
 // ---- float32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float rcp_sign_(float b) { return __fdividef(1.0f, b); }
 // MUFU.LG2-based: absolute error ~1e-6 on |ln x| <= 12 -- after the factors it meets on this path (kappa = 0.29 in the
 // Exner exponent, d(td)/d(ln e) ~ 14 K) that is <= 7e-7 relative, inside the float32 bar of 1e-5; 3 instructions vs 24
 __device__ __forceinline__ float log_(float x) { return __logf(x); }

@@ -56,6 +56,7 @@ struct Consts {
     double wa0, wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4, inv_t0;  // wbpt "direct" rational fit (T:1051-1052)
     double k10, k11, k12, k20, k21, k22, dD1, dD0, c121, c266, c058, c04;  // Davies-Jones first guess (T:1090-1128)
     double t_start, eps_default, neg_lambda, hundred, hundredth, c800, inv_800;
+    double bis_c_ifs, bis_tie, bis_plim_scale;  // lean bisection (ek_thermo_formulas.inc: t_on_ma_bisect_tab_n)
     double g, inv_g, R_earth;  // constants.py:53,57 (height conversions, vertical.py:330-502)
     double degree, radian, two_omega, neg_Rd_g, minus_pi2, pi15;  // wind (constants.py:60-78, wind/array/wind.py)
 };
@@ -135,6 +136,9 @@ constexpr Consts make_consts() {
     k.c04 = 0.4;
     k.t_start = cdef::T0 - 20;  // T:1061
     k.eps_default = 1e-4;
+    k.bis_c_ifs = (-1.0 * cdef::K0_ifs) * cdef::eps;  // G = bis_c_ifs * es / (v t)
+    k.bis_tie = 1e-10;
+    k.bis_plim_scale = 1.0 - 1e-9;
     k.neg_lambda = -cdef::lambda;
     k.hundred = 100.0;
     k.hundredth = 0.01;
