@@ -35,6 +35,14 @@ using namespace ek;
                      // (O1280 x 137 fp64: beyond 2 the 64-register cap spills)
 #endif
 
+// resident CTAs per SM the register budget of the two level-loop kernels is sized for
+#ifndef EK_HYBS_MIN_CTAS
+#define EK_HYBS_MIN_CTAS EK_MIN_CTAS
+#endif
+#ifndef EK_COL_MIN_CTAS
+#define EK_COL_MIN_CTAS EK_MIN_CTAS
+#endif
+
 namespace {
 
 template <typename T> __device__ __forceinline__ bool is_nan_bits(T v);
@@ -104,8 +112,9 @@ template <typename T, bool VECOK>
 __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) hybrid_pressure_kernel(const HybridArgs g) {
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
+    const bool want_da = g.delta != nullptr || g.alpha != nullptr;
 #if EK_LEAN_DEVICE
-    if (sizeof(T) == 8) lean::init_tables();
+    if (sizeof(T) == 8 && want_da) lean::init_tables();  // only delta / alpha take a logarithm (the launch passes no shared memory otherwise)
 #endif
     const T* A = static_cast<const T*>(g.A);
     const T* B = static_cast<const T*>(g.B);
@@ -113,7 +122,6 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) hybrid_pressure_kernel(
     const int n_rows = g.n_full > g.n_half ? g.n_full : g.n_half;
     const int chunks = (n_rows + g.rows_per_item - 1) / g.rows_per_item;
     const int64_t items = ptiles * chunks;
-    const bool want_da = g.delta != nullptr || g.alpha != nullptr;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t pt = it / chunks;
         const int r0 = (int)(it - pt * chunks) * g.rows_per_item;
@@ -168,7 +176,7 @@ struct SuiteHybridArgs {
 };
 
 template <class Op, class OpE, typename T, bool VECOK>
-__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) suite_hybrid_kernel(const SuiteHybridArgs g, const Params P) {
+__global__ void __launch_bounds__(kThreads, EK_HYBS_MIN_CTAS) suite_hybrid_kernel(const SuiteHybridArgs g, const Params P) {
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
     constexpr int LU = EK_HYB_LU;  // levels in flight per thread (their loads are issued before any math)
@@ -249,7 +257,7 @@ struct GeoArgs {
 // (V:799-810, same accumulation order as the reference's flipped cumulative sum).  alpha/delta come from registers
 // (sp, A, B) or from memory (GIVEN_AD).  Loads of two levels are in flight before the math of the lower one.
 template <typename T, bool GIVEN_AD, bool VECOK>
-__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) column_geopotential_kernel(const GeoArgs g) {
+__global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential_kernel(const GeoArgs g) {
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
     constexpr int NARR = GIVEN_AD ? 4 : 2;
@@ -358,10 +366,11 @@ static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhal
     const int blocks = grid_for(items);
     if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
     const bool vec = npl % Vec16<T>::N == 0 && ok16(sp) && ok16(full) && ok16(half) && ok16(delta) && ok16(alpha);
+    const unsigned smem = (delta || alpha) ? smem_for<T>() : 0u;  // the log table, for delta / alpha only
     if (vec)
-        launch_kernel<&hybrid_pressure_kernel<T, true>, T>(blocks, static_cast<cudaStream_t>(stream), g);
+        launch_kernel_smem<&hybrid_pressure_kernel<T, true>>(blocks, static_cast<cudaStream_t>(stream), smem, g);
     else
-        launch_kernel<&hybrid_pressure_kernel<T, false>, T>(blocks, static_cast<cudaStream_t>(stream), g);
+        launch_kernel_smem<&hybrid_pressure_kernel<T, false>>(blocks, static_cast<cudaStream_t>(stream), smem, g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));

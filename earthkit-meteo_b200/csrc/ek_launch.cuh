@@ -41,9 +41,12 @@ template <auto Kernel> inline void prepare_smem(unsigned smem_bytes) {
 }
 
 // prepare_smem + launch of a kernel with the standard CTA size and the dtype's dynamic shared memory
+template <auto Kernel, typename... Args> inline void launch_kernel_smem(int blocks, cudaStream_t st, unsigned smem, Args... args) {
+    prepare_smem<Kernel>(smem);
+    Kernel<<<blocks, kThreads, smem, st>>>(args...);
+}
 template <auto Kernel, typename T, typename... Args> inline void launch_kernel(int blocks, cudaStream_t st, Args... args) {
-    prepare_smem<Kernel>(smem_for<T>());
-    Kernel<<<blocks, kThreads, smem_for<T>(), st>>>(args...);
+    launch_kernel_smem<Kernel>(blocks, st, smem_for<T>(), args...);
 }
 
 // Launch Op over n points.  ins[k].ptr == NULL means broadcast scalar ins[k].value; outs[o] == NULL means
