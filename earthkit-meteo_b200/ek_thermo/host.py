@@ -1,0 +1,145 @@
+"""``ek_thermo.host`` -- the same functions for HOST arrays: numpy in, numpy out, computed on the GPU.
+
+The reference's callers hold numpy arrays (``earthkit.meteo.thermo.array`` is array-namespace code, and
+``xr.apply_ufunc(potential_temperature, t, p)`` hands it the numpy data of xarray objects, reference
+tests/vertical/test_xr_theta.py:34).  This module is the data-format adapter on that side of the path
+(SURVEY.md 8(f)-4): ``host.thermo.<fn>`` and ``host.wind.<fn>`` take what the reference takes -- numpy arrays, nested
+lists, numpy / Python scalars, with numpy broadcasting and dtype promotion -- stream the arrays through the device
+in chunks on two CUDA streams (H2D copy, the one kernel of ``ek_thermo.thermo.<fn>``, D2H copy), and return numpy
+arrays of the broadcast shape.  Options (``method=``, ``phase=``, ``eps=`` ...) and error behaviour are those of the
+device functions, i.e. of the reference.
+
+There is no CPU arithmetic here: without a CUDA device every call raises ``RuntimeError``.  Page-locked inputs /
+outputs (``hostpipe.pinned_empty``) are copied asynchronously at PCIe speed; ordinary (pageable) numpy arrays work
+and are limited by the driver's staging copies.  For the fused suites on whole fields use ``hostpipe.HostSuite``
+(one C call, three streams, no Python per chunk).
+"""
+from __future__ import annotations
+
+import functools
+import math
+
+import numpy as np
+import torch
+
+from . import thermo as _thermo
+from . import wind as _wind
+
+__all__ = ["thermo", "wind", "set_chunk_elements"]
+
+_CHUNK = 1 << 25  # elements per array per chunk (256 MB of float64): bounds device memory, amortises launch latency
+_TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
+
+
+def set_chunk_elements(n):
+    """Elements per array and chunk of the host pipeline (default 2**25).  Returns the previous value."""
+    global _CHUNK
+    old = _CHUNK
+    if int(n) < 1:
+        raise ValueError("set_chunk_elements: n must be >= 1")
+    _CHUNK = int(n)
+    return old
+
+
+def _is_arraylike(v):
+    return isinstance(v, (np.ndarray, list, tuple, np.generic))
+
+
+def _run(fn, args, kwargs, device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("ek_thermo.host: no CUDA device. The arithmetic runs on the GPU only; there is no CPU fallback "
+                           "(use earthkit.meteo for CPU arrays).")
+    args = list(args)
+    kwargs = {k: (v.item() if isinstance(v, np.generic) else v) for k, v in kwargs.items()}  # numpy scalars as options
+    slots = [("a", i) for i, v in enumerate(args) if _is_arraylike(v)] + [("k", k) for k, v in kwargs.items() if _is_arraylike(v)]
+    if not slots:  # all Python numbers: the reference returns a numpy scalar
+        for i, v in enumerate(args):
+            if isinstance(v, (int, float)) and not isinstance(v, bool):
+                args[i] = np.asarray(float(v))
+                slots = [("a", i)]
+                break
+        if not slots:
+            raise TypeError("ek_thermo.host: expected at least one array or number argument")
+
+    def get(slot):
+        return args[slot[1]] if slot[0] == "a" else kwargs[slot[1]]
+
+    def put(slot, v):
+        if slot[0] == "a":
+            args[slot[1]] = v
+        else:
+            kwargs[slot[1]] = v
+
+    arrs = [np.asarray(get(s)) for s in slots]
+    dt = np.result_type(*arrs)  # Python scalars among the arguments do not up-cast float32 arrays (numpy semantics)
+    if dt not in _TORCH:
+        dt = np.dtype("float64")  # integer / bool / float16 input: computed in float64, as numpy would promote
+    shape = np.broadcast_shapes(*[a.shape for a in arrs])
+    n = int(math.prod(shape))
+    flat = []
+    for s, a in zip(slots, arrs):
+        a = a.astype(dt, copy=False)
+        if a.size == 1 and n != 1:
+            put(s, float(a.reshape(-1)[0]))  # broadcast by value inside the kernel, never materialised
+            continue
+        if a.shape != shape:
+            a = np.broadcast_to(a, shape)
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:  # torch.from_numpy wants a writable buffer (it is only read here)
+            a = a.copy()
+        flat.append((s, a.reshape(-1)))
+    if n == 0:
+        probe = fn(*[torch.empty(0, dtype=_TORCH[dt], device=device) if ("a", i) in slots else v for i, v in enumerate(args)],
+                   **{k: (torch.empty(0, dtype=_TORCH[dt], device=device) if ("k", k) in slots else v) for k, v in kwargs.items()})
+        many = isinstance(probe, tuple)
+        outs = [np.empty(shape, dt) for _ in (probe if many else (probe,))]
+        return tuple(outs) if many else outs[0]
+
+    streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+    outs = None
+    many = False
+    chunk = max(1, _CHUNK)
+    for ci, b in enumerate(range(0, n, chunk)):
+        e = min(n, b + chunk)
+        st = streams[ci % 2]
+        with torch.cuda.stream(st):
+            for s, a in flat:
+                put(s, torch.from_numpy(a[b:e]).to(device, non_blocking=True))
+            res = fn(*args, **kwargs)
+            many = isinstance(res, tuple)
+            res = res if many else (res,)
+            if outs is None:
+                outs = [np.empty(n, dt) for _ in res]
+            for o, r in zip(outs, res):
+                torch.from_numpy(o[b:e]).copy_(r.reshape(-1), non_blocking=True)
+    for st in streams:
+        st.synchronize()
+    outs = [o.reshape(shape)[()] if shape == () else o.reshape(shape) for o in outs]
+    return tuple(outs) if many else outs[0]
+
+
+class _HostNamespace:
+    """Attribute access returns the host-array version of the device function of the same name."""
+
+    def __init__(self, module, names, what):
+        self._module = module
+        self.__all__ = list(names)
+        self.__doc__ = f"Host-array (numpy) front end of ``ek_thermo.{what}``: same names, signatures and options."
+        self.device = None  # None: the current CUDA device at call time
+        for name in names:
+            setattr(self, name, self._wrap(getattr(module, name)))
+
+    def _wrap(self, fn):
+        @functools.wraps(fn)
+        def host_fn(*args, **kwargs):
+            dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None and torch.cuda.is_available() else self.device
+            return _run(fn, args, kwargs, dev)
+
+        host_fn.__doc__ = (fn.__doc__ or "") + "\n\nHost-array version: numpy arrays / scalars in, numpy out; computed on the GPU in chunks."
+        return host_fn
+
+
+thermo = _HostNamespace(_thermo, _thermo.__all__, "thermo")
+thermo.array = thermo  # the reference exposes the functions under ``thermo`` and ``thermo.array``
+wind = _HostNamespace(_wind, _wind.__all__, "wind")
+wind.array = wind

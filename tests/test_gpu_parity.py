@@ -556,3 +556,76 @@ def test_lean_math_accuracy_in_ulps(ek):
     # theta's exponent kappa*ln(p0/p) reaches 3.3, so an absolute error of 1 ulp(ln p) shows up as a few ulp of theta
     assert ulps["theta (log, exp)"] < 32 and ulps["td from q (rcp, log, rcp)"] < 32, ulps
     assert ulps["es water (rcp, exp)"] < 64 and ulps["es mixed"] < 64 and ulps["e from q (rcp)"] < 8, ulps
+
+
+def test_host_array_front_end_equals_device_path(ek):
+    """ek_thermo.host (numpy in, numpy out): every case of the table, streamed through the device in
+    ragged chunks on two streams, returns exactly what the device call returns (same kernels), as numpy arrays."""
+    from ek_thermo import host
+
+    inputs = random_inputs(N_RANDOM, seed=5)
+    old = host.set_chunk_elements(10_000)  # 37 965 points -> 4 chunks, the last one ragged
+    try:
+        for case in CASES:
+            args_np = [np.ascontiguousarray(inputs[a].astype(np.float64)) for a in case.args]
+            got = getattr(host.thermo, case.fn)(*args_np, **case.kwargs)
+            want = getattr(ek.thermo, case.fn)(*[torch.from_numpy(a).to(DEV) for a in args_np], **case.kwargs)
+            got, want = (got, want) if isinstance(got, tuple) else ((got,), (want,))
+            assert len(got) == len(want), case.id
+            for g, w in zip(got, want):
+                assert isinstance(g, np.ndarray) and g.dtype == np.float64 and g.shape == args_np[0].shape, case.id
+                assert np.array_equal(g, w.cpu().numpy(), equal_nan=True), case.id
+    finally:
+        host.set_chunk_elements(old)
+
+
+def test_host_array_front_end_numpy_semantics(ek):
+    """Broadcasting, dtype promotion, scalars, lists, pinned buffers and the wind functions through ek_thermo.host."""
+    from ek_thermo import host, hostpipe
+
+    rng = np.random.default_rng(3)
+    t = rng.uniform(220.0, 310.0, (5, 1, 257))
+    p = np.array([1000.0, 5.0e4, 7.0e4, 8.5e4, 1.0e5]).reshape(5, 1, 1) * np.ones((1, 3, 1))
+    with np.errstate(all="ignore"):
+        got = host.thermo.potential_temperature(t, p)  # (5,1,257) x (5,3,1) -> (5,3,257)
+        assert got.shape == (5, 3, 257)
+        np.testing.assert_allclose(got, oracle.potential_temperature(t, p), rtol=1e-12)
+        np.testing.assert_allclose(host.thermo.potential_temperature(t, 8.5e4), oracle.potential_temperature(t, 8.5e4), rtol=1e-12)
+        # float32 stays float32 (a Python scalar does not up-cast), mixed float32 / float64 arrays promote to float64
+        t32 = t.astype(np.float32)
+        g32 = host.thermo.saturation_vapour_pressure(t32)
+        assert g32.dtype == np.float32
+        np.testing.assert_allclose(g32, oracle.saturation_vapour_pressure(t32), rtol=2e-5)
+        assert host.thermo.potential_temperature(t32, p).dtype == np.float64
+        # lists and integers, Python scalars only (numpy scalar out), zero-size input
+        np.testing.assert_allclose(host.thermo.celsius_to_kelvin([0, 10, 20]), [273.16, 283.16, 293.16], rtol=1e-15)
+        s = host.thermo.potential_temperature(280.0, 9.0e4)
+        assert np.ndim(s) == 0 and abs(float(s) - float(oracle.potential_temperature(np.float64(280.0), np.float64(9.0e4)))) < 1e-10
+        assert host.thermo.potential_temperature(np.empty((0, 4)), np.empty((0, 4))).shape == (0, 4)
+        # two outputs, keyword options, errors as in the reference
+        t1, td1, p1 = t[0, 0], t[0, 0] - 5.0, np.full(257, 9.0e4)
+        tl, pl = host.thermo.lcl(t1, td1, p1, method="bolton")
+        wl = oracle.lcl(t1, td1, p1, method="bolton")
+        np.testing.assert_allclose(tl, wl[0], rtol=1e-12)
+        np.testing.assert_allclose(pl, wl[1], rtol=1e-12)
+        with pytest.raises(KeyError):
+            host.thermo.ept_from_dewpoint(t1, td1, p1, method="nope")
+    # page-locked arrays take the asynchronous copy path
+    n = 300_000
+    tp, pp = hostpipe.pinned_empty(n), hostpipe.pinned_empty(n)
+    tp[:] = rng.uniform(220.0, 310.0, n)
+    pp[:] = rng.uniform(1.0e4, 1.0e5, n)
+    old = host.set_chunk_elements(70_000)
+    try:
+        np.testing.assert_allclose(host.thermo.potential_temperature(tp, pp), oracle.potential_temperature(tp, pp), rtol=1e-12)
+    finally:
+        host.set_chunk_elements(old)
+    # wind
+    u, v = rng.normal(0, 10, 1000), rng.normal(0, 10, 1000)
+    np.testing.assert_allclose(host.wind.speed(u, v), np.hypot(u, v), rtol=1e-14)
+    sp_, dir_ = host.wind.xy_to_polar(u, v)
+    np.testing.assert_allclose(sp_, np.hypot(u, v), rtol=1e-14)
+    assert dir_.shape == u.shape and np.all((dir_ >= 0) & (dir_ <= 360))
+    # the device namespace still refuses host arrays: no silent CPU path anywhere
+    with pytest.raises(TypeError):
+        ek.thermo.potential_temperature(t, p)

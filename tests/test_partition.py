@@ -103,3 +103,20 @@ def test_host_binding_helper_without_a_gpu():
         before = os.sched_getaffinity(0)
         assert hostpipe.bind_host_to_device("cuda:0") is None
         assert os.sched_getaffinity(0) == before
+
+
+def test_host_array_front_end_has_no_cpu_path():
+    """ek_thermo.host mirrors the reference's names for numpy input; without a GPU it raises instead of computing on the CPU."""
+    import numpy as np
+    import torch
+
+    from ek_thermo import host, thermo, wind
+
+    assert sorted(host.thermo.__all__) == sorted(thermo.__all__) and sorted(host.wind.__all__) == sorted(wind.__all__)
+    assert host.thermo.array is host.thermo
+    assert host.thermo.potential_temperature.__name__ == "potential_temperature"
+    with pytest.raises(ValueError):
+        host.set_chunk_elements(0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            host.thermo.potential_temperature(np.full(4, 280.0), np.full(4, 9.0e4))
