@@ -194,6 +194,9 @@ static __device__ float2 ek_bisect_tab_f[EK_BISECT_NODES];  // float32 twin: nod
 // ---- float32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ float rcp_sign_(float b) { return __fdividef(1.0f, b); }
+// 1/b in the dtype's lean flavour, for formulas that fold the quotient into an FMA
+__device__ __forceinline__ double rcp_any(double b) { return rcp_(b); }
+__device__ __forceinline__ float rcp_any(float b) { return __fdividef(1.0f, b); }
 // MUFU.LG2-based: absolute error ~1e-6 on |ln x| <= 12 -- after the factors it meets on this path (kappa = 0.29 in the
 // Exner exponent, d(td)/d(ln e) ~ 14 K) that is <= 7e-7 relative, inside the float32 bar of 1e-5; 3 instructions vs 24
 __device__ __forceinline__ float log_(float x) { return __logf(x); }

@@ -629,3 +629,37 @@ def test_host_array_front_end_numpy_semantics(ek):
     # the device namespace still refuses host arrays: no silent CPU path anywhere
     with pytest.raises(TypeError):
         ek.thermo.potential_temperature(t, p)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_fused_results_do_not_depend_on_position(ek, dtype):
+    """A point's result is the same bits whether it is computed in the vector body of a tile or in the scalar tail, in a
+    whole-field launch or in a launch over a piece of the field: the fused suites and the ept / wet-bulb kernel on
+    pieces (ragged, 16-byte aligned and unaligned starts) equal the whole-field launch exactly."""
+    from ek_thermo import fused
+
+    inp = random_inputs(N_RANDOM, seed=11)
+    t, q, p, td = (torch.from_numpy(inp[k]).to(DEV).to(dtype) for k in ("t", "q", "p", "td"))
+    cuts = [0, 10_000, 10_003, 21_111, N_RANDOM]
+
+    def pieces(fn):
+        parts = [fn(slice(b, e)) for b, e in zip(cuts[:-1], cuts[1:])]
+        return [torch.cat([pt[k] for pt in parts]) for k in range(len(parts[0]))]
+
+    def same(whole, parts, what):
+        for k, (w, s) in enumerate(zip(whole, parts)):
+            assert torch.equal(torch.nan_to_num(w, nan=-1.0), torch.nan_to_num(s, nan=-1.0)), (what, k)
+
+    everything = tuple(fused.SUITE_TQP_OUTPUTS)
+    same(list(fused.suite_tqp(t, q, p, outputs=everything).values()),
+         pieces(lambda s: list(fused.suite_tqp(t[s], q[s], p[s], outputs=everything).values())), "suite_tqp")
+    everything = tuple(fused.SUITE_TTDP_OUTPUTS)
+    same(list(fused.suite_ttdp(t, td, p, outputs=everything).values()),
+         pieces(lambda s: list(fused.suite_ttdp(t[s], td[s], p[s], outputs=everything).values())), "suite_ttdp")
+    for em in ("ifs", "bolton35", "bolton39"):
+        for tm in ("direct", "bisect", "newton"):
+            for potential in (True, False):
+                if tm == "direct" and not potential:
+                    continue
+                kw = dict(humidity="q", ept_method=em, t_method=tm, potential=potential)
+                same(list(fused.ept_wet_bulb(t, q, p, **kw)), pieces(lambda s: list(fused.ept_wet_bulb(t[s], q[s], p[s], **kw))), (em, tm, potential))
