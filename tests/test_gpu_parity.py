@@ -440,9 +440,35 @@ def test_exact_build_variant_passes_the_same_parity_cases():
     env = dict(os.environ, EK_THERMO_LIB="libek_thermo_exact.so")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu", "-x", "-k",
-                        "(oracle_random and f64) or (oracle_edge and f64) or fixtures or csv_goldens or fused_suites"],
+                        "(oracle_random and f64) or (oracle_edge and f64) or fixtures or csv_goldens or fused_suites or bit_identical"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_exact_build_is_bit_identical_on_arithmetic_functions(ek):
+    """The exact build (IEEE division, no fused multiply-add: -fmad=false) performs the reference's operations one by one, so
+    every function without a transcendental returns numpy's bits -- random and special-value inputs, float64 and float32.
+    Runs in the child process of test_exact_build_variant_passes_the_same_parity_cases (the product library replaces the
+    division by a reciprocal and is held to 1e-12 instead)."""
+    import os
+
+    if os.path.basename(ek._backend.LIB_PATH) != "libek_thermo_exact.so":
+        pytest.skip("only meaningful for the exact build")
+    arithmetic = {"celsius_to_kelvin", "kelvin_to_celsius", "specific_humidity_from_mixing_ratio", "mixing_ratio_from_specific_humidity",
+                  "vapour_pressure_from_specific_humidity", "vapour_pressure_from_mixing_ratio", "specific_humidity_from_vapour_pressure",
+                  "mixing_ratio_from_vapour_pressure", "virtual_temperature", "specific_gas_constant"}
+    checked = 0
+    for case in CASES:
+        if case.fn not in arithmetic:
+            continue
+        for dtype in (np.float64, np.float32):
+            for inputs in (random_inputs(N_RANDOM, seed=5), edge_inputs(n=4099, seed=21)):
+                with np.errstate(all="ignore"):
+                    got, want, _ = _run_case(ek, case, inputs, dtype)
+                for g, w in zip(got, want):
+                    assert np.array_equal(g, np.asarray(w, dtype=dtype), equal_nan=True), (case.id, dtype.__name__)
+                    checked += 1
+    assert checked >= 4 * len(arithmetic)
 
 
 def test_cuda_graph_capture_and_replay(ek):
