@@ -227,14 +227,29 @@ def _prepare(args):
     return ops, keep, dtype, dev, shape, n
 
 
+# torch's raw accessors (no Stream / device objects built per call): the eager ERA5-level call is bound by host time
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+_FN_CACHE = {}
+
+
+def _stream_ptr(device):
+    if _raw_stream is not None:
+        return _raw_stream(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def _call(symbol: str, dtype, device, c_args):
     """The one place where the C ABI is entered.  (Tests patch this to check the host logic on CPU.)"""
-    fn = getattr(_lib, f"ek_thermo_{symbol}_{_SUFFIX[dtype]}")
-    if torch.cuda.current_device() == device.index:  # the usual case: no device switch needed
-        _check(fn(*c_args, c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    fn = _FN_CACHE.get((symbol, dtype))
+    if fn is None:
+        fn = _FN_CACHE[(symbol, dtype)] = getattr(_lib, f"ek_thermo_{symbol}_{_SUFFIX[dtype]}")
+    cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+    if cur == device.index:  # the usual case: no device switch needed
+        _check(fn(*c_args, c_void_p(_stream_ptr(device))))
         return
     with torch.cuda.device(device):
-        _check(fn(*c_args, c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        _check(fn(*c_args, c_void_p(_stream_ptr(device))))
 
 
 def call_raw(symbol: str, dtype, device, *c_args):
