@@ -53,6 +53,12 @@ template <typename T> __device__ __noinline__ void exact_delta_alpha(T ph0, T ph
     exactm::hyb_delta_alpha<T>(ph0, ph1, top, at, *d, *a);
 }
 
+// cold path of the column kernel's output form: out of line, so the six-way switch with IEEE divisions stays out of the
+// level loop (inlined it was most of the loop's 1680 instructions and pushed the kernel into spills)
+template <typename T> __device__ __noinline__ T exact_height_output(T dphi, T zs, int mode) {
+    return exactm::height_output(dphi, zs, exactm::geom_from_z(zs), mode);
+}
+
 template <typename T> __device__ __forceinline__ void delta_alpha(T ph0, T ph1, bool top, T at, T& d, T& a) {
 #if EK_LEAN_DEVICE
     fastm::hyb_delta_alpha<T>(ph0, ph1, top, at, d, a);
@@ -70,7 +76,7 @@ template <typename T> __device__ __forceinline__ void delta_alpha(T ph0, T ph1, 
 // loads / stores of one thread's VEC consecutive points of a row; vector path when aligned and in range
 template <typename T, bool VECOK> __device__ __forceinline__ void ld_row(const T* row, int64_t i0, int64_t npl, T* v, bool streaming) {
     constexpr int VEC = Vec16<T>::N;
-    if (VECOK && i0 + VEC <= npl) {
+    if (VECOK) {  // the vector instantiation is only launched when npl is a multiple of VEC: i0 < npl implies the whole vector is in range
         if (streaming) {
             Vec16<T>::load(row + i0, v);
         } else {
@@ -84,7 +90,7 @@ template <typename T, bool VECOK> __device__ __forceinline__ void ld_row(const T
 }
 template <typename T, bool VECOK> __device__ __forceinline__ void st_row(T* row, int64_t i0, int64_t npl, const T* v) {
     constexpr int VEC = Vec16<T>::N;
-    if (VECOK && i0 + VEC <= npl) {
+    if (VECOK) {
         Vec16<T>::store(row + i0, v);
     } else {
 #pragma unroll
@@ -256,8 +262,11 @@ struct GeoArgs {
 // One thread walks VEC columns from the bottom level to the top one: d = R(q) t, dphi_k = sum_{j>k} d_j delta_j + d_k alpha_k
 // (V:799-810, same accumulation order as the reference's flipped cumulative sum).  alpha/delta come from registers
 // (sp, A, B) or from memory (GIVEN_AD).  Loads of two levels are in flight before the math of the lower one.
-template <typename T, bool GIVEN_AD, bool VECOK>
+// MODE >= 0: the output form is a compile-time constant (the registers of zs / geom(zs) and the form choices drop out of
+// the level loop where they are not needed); MODE = -1: taken from g.mode at run time (the rarer launch shapes).
+template <typename T, bool GIVEN_AD, bool VECOK, int MODE>
 __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential_kernel(const GeoArgs g) {
+    const int mode = MODE >= 0 ? MODE : g.mode;
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
     constexpr int NARR = GIVEN_AD ? 4 : 2;
@@ -272,14 +281,19 @@ __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential
     for (int64_t pt = blockIdx.x; pt < ptiles; pt += gridDim.x) {
         const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
         if (i0 >= g.npl) continue;
-        T sp[VEC], zs[VEC], hs[VEC], sum[VEC];
+        T sp[VEC], zs[VEC], hsub[VEC], sum[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) sp[j] = zs[j] = hs[j] = sum[j] = T(0);
+        for (int j = 0; j < VEC; ++j) sp[j] = zs[j] = hsub[j] = sum[j] = T(0);
         if (!GIVEN_AD) ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
-        if (g.zs != nullptr) ld_row<T, VECOK>(static_cast<const T*>(g.zs), i0, g.npl, zs, false);
-        if (g.mode == EK_HM_GEOM_GROUND) {
+        const bool add_zs = mode != EK_HM_THICKNESS && mode != EK_HM_GH_GROUND;
+        if (add_zs) ld_row<T, VECOK>(static_cast<const T*>(g.zs), i0, g.npl, zs, false);
+        // The six output forms (V:1064-1069, V:1163-1188) as one expression: z = dphi (+ zs), then nothing / z/g / the
+        // geometric height of z minus hsub (geom(zs) or 0: subtracting 0 changes no bit), so the level loop carries
+        // warp-uniform two- and three-way choices instead of a six-way switch.
+        const int form = mode >> 1;  // 0: geopotential units, 1: geopotential height, 2: geometric height
+        if (mode == EK_HM_GEOM_GROUND) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) hs[j] = EK_FAST_NS::geom_from_z(zs[j]);
+            for (int j = 0; j < VEC; ++j) hsub[j] = EK_FAST_NS::geom_from_z(zs[j]);
         }
         for (int k = g.nlev - 1; k >= 0; k -= CLU) {
             T x[CLU][NARR][VEC];
@@ -309,11 +323,13 @@ __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential
                         delta_alpha<T>(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]), top, static_cast<T>(g.alpha_top), de, al);
                     }
                     const T d = exactm::gas_constant(x[u][1][j]) * x[u][0][j];
-                    const T dphi = (kk == g.nlev - 1) ? d * al : sum[j] + d * al;  // V:808-809
-                    sum[j] = (kk == g.nlev - 1) ? d * de : sum[j] + d * de;        // V:804 (running sum of d * delta below this layer)
-                    T h = EK_FAST_NS::height_output(dphi, zs[j], hs[j], g.mode);
+                    // the running sum starts at 0: 0 + x is x, so the bottom level needs no special case
+                    const T dphi = sum[j] + d * al;  // V:808-809
+                    sum[j] = sum[j] + d * de;        // V:804 (running sum of d * delta below this layer)
+                    const T z = add_zs ? dphi + zs[j] : dphi;
+                    T h = form == 0 ? z : (form == 1 ? EK_FAST_NS::gh_from_z(z) : EK_FAST_NS::geom_from_z(z) - hsub[j]);
 #if EK_LEAN_DEVICE
-                    if (sizeof(T) == 8 && __builtin_expect(is_nan_bits(h), 0)) h = exactm::height_output(dphi, zs[j], exactm::geom_from_z(zs[j]), g.mode);
+                    if (sizeof(T) == 8 && __builtin_expect(is_nan_bits(h), 0)) h = exact_height_output<T>(dphi, zs[j], mode);
 #endif
                     y[j] = h;
                 }
@@ -413,11 +429,19 @@ static int impl_geopotential_on_hybrid_levels(const void* t, const void* q, int 
     const bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(alpha) && ok16(delta) && ok16(zs) && ok16(out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (given) {
-        if (vec) launch_kernel<&column_geopotential_kernel<T, true, true>, T>(blocks, st, g);
-        else launch_kernel<&column_geopotential_kernel<T, true, false>, T>(blocks, st, g);
-    } else {
-        if (vec) launch_kernel<&column_geopotential_kernel<T, false, true>, T>(blocks, st, g);
-        else launch_kernel<&column_geopotential_kernel<T, false, false>, T>(blocks, st, g);
+        if (vec) launch_kernel<&column_geopotential_kernel<T, true, true, -1>, T>(blocks, st, g);
+        else launch_kernel<&column_geopotential_kernel<T, true, false, -1>, T>(blocks, st, g);
+    } else if (!vec) {
+        launch_kernel<&column_geopotential_kernel<T, false, false, -1>, T>(blocks, st, g);
+    } else {  // the whole-field case: one instantiation per output form
+        switch (mode) {
+            case EK_HM_THICKNESS: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_THICKNESS>, T>(blocks, st, g); break;
+            case EK_HM_GEOPOTENTIAL: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOPOTENTIAL>, T>(blocks, st, g); break;
+            case EK_HM_GH_SEA: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GH_SEA>, T>(blocks, st, g); break;
+            case EK_HM_GH_GROUND: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GH_GROUND>, T>(blocks, st, g); break;
+            case EK_HM_GEOM_SEA: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_SEA>, T>(blocks, st, g); break;
+            default: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_GROUND>, T>(blocks, st, g); break;
+        }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();

@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--masked", type=float, default=0.0, help="fraction of points (contiguous blocks) set to NaN in every input")
     ap.add_argument("--graph", action="store_true", help="also time the fused suites replayed from a CUDA graph")
     ap.add_argument("--realistic", action="store_true", help="IFS-like smooth t(p) instead of uniform random t")
+    ap.add_argument("--smooth", action="store_true",
+                    help="spatially smooth fields (neighbouring points differ by ~1e-4 relative, as analysed fields do): warps stay "
+                         "phase-uniform and read neighbouring table entries; the default inputs are random per point (SURVEY 8(d))")
     a = ap.parse_args()
     dt = torch.float64 if a.dtype == "f64" else torch.float32
     esz = 8 if a.dtype == "f64" else 4
@@ -37,13 +40,26 @@ def main():
     n = a.points
     g = torch.Generator(device=dev).manual_seed(0)
     p = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0e3, 1.05e5, generator=g)
-    if a.realistic:
+    if a.smooth:  # long waves along the array + 0.01 % noise
+        x = torch.arange(n, device=dev, dtype=torch.float64) * (2.0 * 3.141592653589793 / n)
+        wob = lambda lo, hi: 1.0 + torch.empty(n, device=dev, dtype=torch.float64).uniform_(lo, hi, generator=g)  # noqa: E731
+        p = (5.3e4 + 5.0e4 * torch.sin(7.0 * x)) * wob(-1e-4, 1e-4)
+        t = (288.15 * (p / 101325.0) ** 0.19 + 10.0 * torch.sin(131.0 * x)).clamp_(180, 320) * wob(-1e-4, 1e-4)
+        del x
+    elif a.realistic:
         t = (288.15 * (p / 101325.0) ** 0.19 + torch.empty(n, device=dev, dtype=torch.float64).uniform_(-15, 15, generator=g)).clamp_(180, 320)
     else:
         t = torch.empty(n, device=dev, dtype=torch.float64).uniform_(200.0, 320.0, generator=g)
-    q = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
-    td = t - torch.empty(n, device=dev, dtype=torch.float64).uniform_(0.0, 30.0, generator=g)
-    r = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0, 100.0, generator=g)
+    if a.smooth:
+        x = torch.arange(n, device=dev, dtype=torch.float64) * (2.0 * 3.141592653589793 / n)
+        q = (0.0101 + 0.0099 * torch.sin(53.0 * x)) * wob(-1e-4, 1e-4)
+        td = t - (15.0 + 14.0 * torch.sin(29.0 * x))
+        r = (50.5 + 49.0 * torch.sin(17.0 * x)) * wob(-1e-4, 1e-4)
+        del x
+    else:
+        q = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
+        td = t - torch.empty(n, device=dev, dtype=torch.float64).uniform_(0.0, 30.0, generator=g)
+        r = torch.empty(n, device=dev, dtype=torch.float64).uniform_(1.0, 100.0, generator=g)
     if a.masked > 0:  # missing values in contiguous blocks of 64 Ki points
         m = (torch.arange(n, device=dev) // 65536) % 100 < int(a.masked * 100)
         for x in (t, p, q, td, r):
@@ -78,7 +94,7 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    print(f"lib={ek_thermo._backend.LIB_PATH} dtype={a.dtype} n={n} realistic={a.realistic} peak={peak} GB/s")
+    print(f"lib={ek_thermo._backend.LIB_PATH} dtype={a.dtype} n={n} realistic={a.realistic} smooth={a.smooth} peak={peak} GB/s")
     for ctas in [int(c) for c in a.ctas.split(",")]:
         ek_thermo.set_launch_config(0, ctas)
         for name, (fn, narr) in kernels.items():
