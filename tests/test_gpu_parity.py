@@ -712,3 +712,28 @@ def test_fused_results_do_not_depend_on_position(ek, dtype):
                     continue
                 kw = dict(humidity="q", ept_method=em, t_method=tm, potential=potential)
                 same(list(fused.ept_wet_bulb(t, q, p, **kw)), pieces(lambda s: list(fused.ept_wet_bulb(t[s], q[s], p[s], **kw))), (em, tm, potential))
+
+
+def test_more_than_2_to_31_points_in_one_launch(ek):
+    """Maximum sizes: indexing is 64-bit end to end.  One launch over 2^31 + 4099 float32 points (8.6 GB in, 8.6 GB out),
+    once through a one-input kernel and once through a two-input kernel with a broadcast scalar; the points beyond the
+    32-bit boundary, the ragged tail and a strided sample are checked against the oracle."""
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 31) + 4099
+    if free < 3 * 4 * n + (1 << 30):
+        pytest.skip("not enough free device memory for a 2^31-point field")
+    t = torch.empty(n, dtype=torch.float32, device=DEV)
+    t[: 1 << 20] = torch.linspace(200.0, 320.0, 1 << 20, device=DEV)
+    t[1 << 20:] = 250.0
+    t[-4099:] = torch.linspace(210.0, 310.0, 4099, device=DEV)
+    t[(1 << 31) - 5: (1 << 31) + 5] = torch.arange(10, device=DEV, dtype=torch.float32) + 270.0
+    k = ek.thermo.kelvin_to_celsius(t)
+    th = ek.thermo.potential_temperature(t, 85000.0)
+    torch.cuda.synchronize()
+    idx = torch.cat([torch.arange(0, 4096, device=DEV), torch.arange((1 << 31) - 8, n, device=DEV), torch.arange(0, n, 104729, device=DEV)])
+    tin = t[idx].cpu().numpy()
+    np.testing.assert_array_equal(k[idx].cpu().numpy(), oracle.kelvin_to_celsius(tin))
+    np.testing.assert_allclose(th[idx].cpu().numpy(), oracle.potential_temperature(tin, np.float32(85000.0)), rtol=2e-6)
+    assert k.shape == t.shape and th.shape == t.shape
+    del t, k, th
+    torch.cuda.empty_cache()
