@@ -81,7 +81,8 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     if (n == 0) return EK_OK;
 
     constexpr int threads = kThreads;
-    const int64_t tile = (int64_t)threads * Vec16<T>::N * EK_UNROLL;
+    constexpr int unroll = UnrollOf<Op>::value;
+    const int64_t tile = (int64_t)threads * Vec16<T>::N * unroll;
     const int64_t ntiles = n / tile;
     const int64_t tail_blocks = ((n - ntiles * tile) + threads - 1) / threads;
     const int sms = sm_count_current_device();
@@ -91,8 +92,8 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
 
-    prepare_smem<&ew_kernel<Op, OpE, T, EK_UNROLL>>(smem_for<T>());
-    ew_kernel<Op, OpE, T, EK_UNROLL><<<(unsigned)blocks, threads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
+    prepare_smem<&ew_kernel<Op, OpE, T, unroll>>(smem_for<T>());
+    ew_kernel<Op, OpE, T, unroll><<<(unsigned)blocks, threads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));

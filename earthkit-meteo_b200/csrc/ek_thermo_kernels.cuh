@@ -183,6 +183,15 @@ __device__ __forceinline__ void points_n(const T (&a)[N][Op::NIN], T (&r)[N][Op:
 #endif
 }
 
+// 16-byte vectors per input per thread per tile: EK_UNROLL unless the functor declares `UNROLL` (the one-step Newton solve keeps
+// one vector in flight: its ~550-instruction body needs the registers, and without spills it runs 8-12 % faster).
+template <class Op, class = void> struct UnrollOf {
+    static constexpr int value = EK_UNROLL;
+};
+template <class Op> struct UnrollOf<Op, decltype((void)Op::UNROLL)> {
+    static constexpr int value = Op::UNROLL > 0 ? Op::UNROLL : EK_UNROLL;
+};
+
 // The inputs of one tile, per thread: UNROLL 16-byte vectors of every input array, in registers.
 template <class Op, typename T, int UNROLL> struct TileRegs {
     T x[Op::NIN][UNROLL][Vec16<T>::N];
