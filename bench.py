@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--levels", type=int, default=0, help="override the number of levels (smaller field)")
     ap.add_argument("--e2e-levels", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-workspace-mb", type=int, default=1536)
+    ap.add_argument("--e2e-workspace-mb", type=int, default=768)
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU baseline leg")
     args = ap.parse_args()
     kind, outputs, levels, npl, dtype = WORKLOADS[args.workload]
