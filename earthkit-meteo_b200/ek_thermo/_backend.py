@@ -167,7 +167,44 @@ def _check_device(tensors):
     return dev
 
 
+_Tensor = torch.Tensor
+
+
+def _on_device(t):
+    return t.is_cuda
+
+
 def _prepare(args):
+    """Operands of a launch.  Fast path for the normal whole-field call -- every array argument a contiguous CUDA tensor
+    of one dtype (float64 / float32), shape and device, the rest Python numbers -- and `_prepare_general` for everything
+    else (broadcasting, promotion, non-contiguous views, errors).  The eager call of a 1 M-point field is bound by this
+    host code, not by the kernel."""
+    first = None
+    ops = []
+    for a in args:
+        if isinstance(a, _Tensor):
+            if first is None:
+                first = a
+                dtype = a.dtype
+                shape = a.shape
+                dev = a.device
+                if dtype not in _SUFFIX:
+                    return _prepare_general(args)
+            elif a.dtype != dtype or a.shape != shape or a.device != dev:
+                return _prepare_general(args)
+            if not a.is_contiguous():
+                return _prepare_general(args)
+            ops.append(ek_operand(a.data_ptr(), 0.0))
+        elif type(a) is float:
+            ops.append(ek_operand(None, a))
+        else:
+            return _prepare_general(args)
+    if first is None or not _on_device(first):
+        return _prepare_general(args)  # raises the TypeError of the no-CPU-path rule
+    return ops, (), dtype, dev, shape, first.numel()
+
+
+def _prepare_general(args):
     """Split positional array-likes into (tensors | python scalars), find dtype, device, broadcast shape."""
     items = []
     tensors = []
@@ -246,10 +283,12 @@ def _call(symbol: str, dtype, device, c_args):
         fn = _FN_CACHE[(symbol, dtype)] = getattr(_lib, f"ek_thermo_{symbol}_{_SUFFIX[dtype]}")
     cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
     if cur == device.index:  # the usual case: no device switch needed
-        _check(fn(*c_args, c_void_p(_stream_ptr(device))))
+        rc = fn(*c_args, _stream_ptr(device))
+        if rc != 0:
+            _check(rc)
         return
     with torch.cuda.device(device):
-        _check(fn(*c_args, c_void_p(_stream_ptr(device))))
+        _check(fn(*c_args, _stream_ptr(device)))
 
 
 def call_raw(symbol: str, dtype, device, *c_args):
@@ -265,17 +304,24 @@ def execute(symbol: str, args, options=(), want=None):
     """Run entry point `symbol` on positional array args; returns a tensor or a tuple of tensors.
 
     `want` optionally selects which outputs to allocate (tuple of bools), for the two-output kernels.
+    Pointers, sizes and options are handed to ctypes as plain ints (the entry points' argtypes convert them).
     """
     nin, opt_types, nout = SIGNATURES[symbol]
     assert len(args) == nin and len(options) == len(opt_types), symbol
     ops, keep, dtype, dev, shape, n = _prepare(args)
+    if nout == 1:  # the common case: one output, no selection
+        o = torch.empty(shape, dtype=dtype, device=dev)
+        if n > 0:  # empty in -> empty out, nothing to launch (empty tensors have a NULL data_ptr)
+            _call(symbol, dtype, dev, [*ops, *options, o.data_ptr(), n])
+        del keep
+        return o
     if want is None:
         want = (True,) * nout
     outs = [_empty(shape, dtype, dev) if w else None for w in want]
-    c_args = list(ops) + [ct(v) for ct, v in zip(opt_types, options)]
-    c_args += [c_void_p(o.data_ptr()) if o is not None else c_void_p(None) for o in outs]
-    c_args.append(c_int64(n))
-    if n > 0:  # empty in -> empty out, nothing to launch (empty tensors have a NULL data_ptr)
+    c_args = [*ops, *options]
+    c_args += [o.data_ptr() if o is not None else None for o in outs]
+    c_args.append(n)
+    if n > 0:
         _call(symbol, dtype, dev, c_args)
     del keep
     res = tuple(o for o in outs if o is not None)
@@ -289,18 +335,17 @@ def execute_suite(symbol: str, args, out_names, slots, out=None):
     mask = 0
     res = {}
     for name, k in zip(out_names, slots):
-        if out is not None and name in out:
-            t = out[name]
+        t = out.get(name) if out is not None else None
+        if t is not None:
             if t.dtype != dtype or t.shape != shape or not t.is_contiguous() or t.device != dev:
                 raise ValueError(f"ek_thermo: preallocated output {name!r} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
         else:
-            t = _empty(shape, dtype, dev)
+            t = torch.empty(shape, dtype=dtype, device=dev)
         res[name] = t
         ptrs[k] = t.data_ptr()
         mask |= 1 << k
-    c_args = list(ops) + [ctypes.cast(ptrs, ctypes.POINTER(c_void_p)), c_uint32(mask), c_int64(n)]
     if n > 0:
-        _call(symbol, dtype, dev, c_args)
+        _call(symbol, dtype, dev, [*ops, ptrs, mask, n])
     del keep
     return res
 

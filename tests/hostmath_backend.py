@@ -57,14 +57,14 @@ def fake_call(symbol, dtype, device, c_args):
 
     if symbol in ("suite_tqp", "suite_ttdp"):
         operands, (outs, mask, n) = c_args[:3], c_args[3:]
-        mask = mask.value
+        mask = _val(mask)
         o = [outs[k] if (mask >> k) & 1 else None for k in range(8)]
-        return _run(symbol, dtype, operands, o, n.value, mask=mask)
+        return _run(symbol, dtype, operands, o, _val(n), mask=mask)
     nin, opt_types, nout = b.SIGNATURES[symbol]
     operands = c_args[:nin]
     opts = [_val(x) for x in c_args[nin:nin + len(opt_types)]]
     outs = c_args[nin + len(opt_types):nin + len(opt_types) + nout]
-    n = c_args[-1].value
+    n = _val(c_args[-1])
     kw = {}
     op = symbol
     if symbol in ("specific_humidity_from_vapour_pressure", "mixing_ratio_from_vapour_pressure"):
