@@ -9,10 +9,12 @@ in chunks on two CUDA streams (H2D copy, the one kernel of ``ek_thermo.thermo.<f
 arrays of the broadcast shape.  Options (``method=``, ``phase=``, ``eps=`` ...) and error behaviour are those of the
 device functions, i.e. of the reference.
 
-There is no CPU arithmetic here: without a CUDA device every call raises ``RuntimeError``.  Page-locked inputs /
-outputs (``hostpipe.pinned_empty``) are copied asynchronously at PCIe speed; ordinary (pageable) numpy arrays work
-and are limited by the driver's staging copies.  For the fused suites on whole fields use ``hostpipe.HostSuite``
-(one C call, three streams, no Python per chunk).
+There is no CPU arithmetic here: without a CUDA device every call raises ``RuntimeError``.  Arrays of 4 Mi elements
+or more go through page-locked staging buffers that worker threads fill and drain (a pageable ``cudaMemcpy`` is limited
+to 7-8 GB/s by the driver's single staging buffer); page-locked inputs (``hostpipe.pinned_empty``) are copied directly.
+Measured on one B200: 0.75-0.81 Gpt/s for pageable float64 arrays (0.22-0.30 without the staging threads), against
+0.010 Gpt/s for the reference on one core.  For the fused suites on whole fields use ``hostpipe.HostSuite`` (one C
+call, three streams, no Python per chunk).
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ import torch
 from . import thermo as _thermo
 from . import wind as _wind
 
-__all__ = ["thermo", "wind", "set_chunk_elements"]
+__all__ = ["thermo", "wind", "set_chunk_elements", "release_staging"]
 
 _CHUNK = 1 << 25  # elements per array per chunk (256 MB of float64): bounds device memory, amortises launch latency
 _TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
@@ -95,6 +97,16 @@ def _run(fn, args, kwargs, device):
         outs = [np.empty(shape, dt) for _ in (probe if many else (probe,))]
         return tuple(outs) if many else outs[0]
 
+    if n >= _STAGE_MIN:
+        outs, many = _pipeline_staged(fn, args, kwargs, put, flat, dt, n, device)
+    else:
+        outs, many = _pipeline_direct(fn, args, kwargs, put, flat, dt, n, device)
+    outs = [o.reshape(shape)[()] if shape == () else o.reshape(shape) for o in outs]
+    return tuple(outs) if many else outs[0]
+
+
+def _pipeline_direct(fn, args, kwargs, put, flat, dt, n, device):
+    """Chunks copied straight from / to the caller's arrays on two streams (asynchronous when they are page-locked)."""
     streams = [torch.cuda.Stream(device=device) for _ in range(2)]
     outs = None
     many = False
@@ -114,8 +126,92 @@ def _run(fn, args, kwargs, device):
                 torch.from_numpy(o[b:e]).copy_(r.reshape(-1), non_blocking=True)
     for st in streams:
         st.synchronize()
-    outs = [o.reshape(shape)[()] if shape == () else o.reshape(shape) for o in outs]
-    return tuple(outs) if many else outs[0]
+    return outs, many
+
+
+# ---- staged pipeline for large pageable arrays ---------------------------------------------------------------------
+# A pageable cudaMemcpy goes through the driver's single staging buffer at 7-8 GB/s.  Here worker threads copy each
+# chunk into page-locked staging buffers (numpy releases the GIL for the copy), the copies to and from the device are
+# asynchronous on the slot's stream, and other workers copy finished chunks out of staging into the result arrays (which
+# also spreads the first-touch page faults of the fresh result arrays over several cores).  Three slots keep the three
+# stages of successive chunks overlapped.
+_STAGE_MIN = 1 << 22    # elements: below this the direct path is used
+_STAGE_CHUNK = 1 << 22  # elements per array and staged chunk (32 MB of float64)
+_STAGE_SLOTS = 3
+_pool = None
+_staging = {}  # (dtype, slot, role, k) -> page-locked tensor of _STAGE_CHUNK elements
+
+
+def _workers():
+    global _pool
+    if _pool is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        _pool = ThreadPoolExecutor(max_workers=max(2, min(8, len(os.sched_getaffinity(0)))), thread_name_prefix="ek_host")
+    return _pool
+
+
+def _stage_buf(dt, slot, role, k):
+    key = (dt, slot, role, k)
+    t = _staging.get(key)
+    if t is None:
+        t = _staging[key] = torch.empty(_STAGE_CHUNK, dtype=_TORCH[dt], pin_memory=True)
+    return t
+
+
+def release_staging():
+    """Free the page-locked staging buffers of the host pipeline (they are kept between calls)."""
+    _staging.clear()
+
+
+def _pipeline_staged(fn, args, kwargs, put, flat, dt, n, device):
+    pool = _workers()
+    pinned = [torch.from_numpy(a[:1]).is_pinned() for _, a in flat]  # the caller's own page-locked arrays skip staging
+    streams = [torch.cuda.Stream(device=device) for _ in range(_STAGE_SLOTS)]
+    events = [torch.cuda.Event() for _ in range(_STAGE_SLOTS)]
+    pending = [[] for _ in range(_STAGE_SLOTS)]  # copy-out futures of the chunk that used the slot last
+    ranges = [None] * _STAGE_SLOTS
+    outs = None
+    many = False
+    nres = 0
+
+    def copy_out(slot):
+        b, e = ranges[slot]
+        events[slot].synchronize()
+        pending[slot] = [pool.submit(np.copyto, outs[j][b:e], _stage_buf(dt, slot, "out", j).numpy()[: e - b]) for j in range(nres)]
+
+    for ci, b in enumerate(range(0, n, _STAGE_CHUNK)):
+        e = min(n, b + _STAGE_CHUNK)
+        m = e - b
+        slot = ci % _STAGE_SLOTS
+        for f in pending[slot]:
+            f.result()  # the slot's staging buffers are free again
+        pending[slot] = []
+        futs = [pool.submit(np.copyto, _stage_buf(dt, slot, "in", k).numpy()[:m], a[b:e]) for k, (_, a) in enumerate(flat) if not pinned[k]]
+        for f in futs:
+            f.result()
+        with torch.cuda.stream(streams[slot]):
+            for k, (s, a) in enumerate(flat):
+                src = torch.from_numpy(a[b:e]) if pinned[k] else _stage_buf(dt, slot, "in", k)[:m]
+                put(s, src.to(device, non_blocking=True))
+            res = fn(*args, **kwargs)
+            many = isinstance(res, tuple)
+            res = res if many else (res,)
+            if outs is None:
+                nres = len(res)
+                outs = [np.empty(n, dt) for _ in res]
+            for j, r in enumerate(res):
+                _stage_buf(dt, slot, "out", j)[:m].copy_(r.reshape(-1), non_blocking=True)
+            events[slot].record()
+        ranges[slot] = (b, e)
+        if ci > 0:  # the previous chunk has had this chunk's staging time to finish on the device
+            copy_out((ci - 1) % _STAGE_SLOTS)
+    copy_out(ci % _STAGE_SLOTS)
+    for p in pending:
+        for f in p:
+            f.result()
+    return outs, many
 
 
 class _HostNamespace:

@@ -737,3 +737,35 @@ def test_more_than_2_to_31_points_in_one_launch(ek):
     assert k.shape == t.shape and th.shape == t.shape
     del t, k, th
     torch.cuda.empty_cache()
+
+
+def test_host_array_staged_pipeline_equals_device_path(ek):
+    """Large pageable arrays go through page-locked staging buffers filled and drained by worker threads (three slots in
+    flight).  With the thresholds lowered so that 37 965 points make four ragged chunks: same bits as the device call, for
+    one- and two-output functions, float64 and float32, a page-locked input among pageable ones, and repeated calls that
+    reuse the staging buffers."""
+    from ek_thermo import host, hostpipe
+
+    inputs = random_inputs(N_RANDOM, seed=9)
+    old = (host._STAGE_MIN, host._STAGE_CHUNK)
+    host._STAGE_MIN, host._STAGE_CHUNK = 20_000, 10_000
+    host.release_staging()
+    try:
+        for dtype in (np.float64, np.float32):
+            t, td, q, p = (np.ascontiguousarray(inputs[k].astype(dtype)) for k in ("t", "td", "q", "p"))
+            tp = hostpipe.pinned_empty(t.size, dtype)
+            tp[:] = t
+            d = {k: torch.from_numpy(v).to(DEV) for k, v in (("t", t), ("td", td), ("q", q), ("p", p))}
+            for _ in range(2):
+                got = host.thermo.relative_humidity_from_specific_humidity(tp, q, p)  # pinned t, pageable q and p
+                want = ek.thermo.relative_humidity_from_specific_humidity(d["t"], d["q"], d["p"])
+                assert got.dtype == dtype and np.array_equal(got, want.cpu().numpy(), equal_nan=True)
+                gl = host.thermo.lcl(t, td, p)
+                wl = ek.thermo.lcl(d["t"], d["td"], d["p"])
+                assert all(np.array_equal(g, w.cpu().numpy(), equal_nan=True) for g, w in zip(gl, wl))
+                gw = host.thermo.wet_bulb_temperature_from_specific_humidity(t, q, 85000.0)  # scalar operand, bisection
+                ww = ek.thermo.wet_bulb_temperature_from_specific_humidity(d["t"], d["q"], 85000.0)
+                assert np.array_equal(gw, ww.cpu().numpy(), equal_nan=True)
+    finally:
+        host._STAGE_MIN, host._STAGE_CHUNK = old
+        host.release_staging()
