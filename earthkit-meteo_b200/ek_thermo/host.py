@@ -24,10 +24,11 @@ import math
 import numpy as np
 import torch
 
+from . import fused as _fused
 from . import thermo as _thermo
 from . import wind as _wind
 
-__all__ = ["thermo", "wind", "set_chunk_elements", "release_staging"]
+__all__ = ["thermo", "wind", "fused", "set_chunk_elements", "release_staging"]
 
 _CHUNK = 1 << 25  # elements per array per chunk (256 MB of float64): bounds device memory, amortises launch latency
 _TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
@@ -44,7 +45,9 @@ def set_chunk_elements(n):
 
 
 def _is_arraylike(v):
-    return isinstance(v, (np.ndarray, list, tuple, np.generic))
+    if isinstance(v, (list, tuple)):  # nested numbers are arrays; ("theta", "rh") is an option
+        return not (len(v) > 0 and isinstance(v[0], str))
+    return isinstance(v, (np.ndarray, np.generic))
 
 
 def _run(fn, args, kwargs, device):
@@ -235,6 +238,34 @@ class _HostNamespace:
         return host_fn
 
 
+class _HostFused:
+    """Host-array versions of the fused kernels: one pass over PCIe for all requested fields."""
+
+    device = None
+
+    def _dev(self):
+        return torch.device("cuda", torch.cuda.current_device()) if self.device is None and torch.cuda.is_available() else self.device
+
+    def _suite(self, fn, a, b, c, outputs):
+        outputs = tuple(outputs)
+        res = _run(lambda x, y, z: tuple(fn(x, y, z, outputs=outputs).values()), (a, b, c), {}, self._dev())
+        return dict(zip(outputs, res if isinstance(res, tuple) else (res,)))
+
+    def suite_tqp(self, t, q, p, outputs=_fused.DEFAULT_TQP):
+        """``fused.suite_tqp`` for numpy arrays: returns ``{name: numpy array}``."""
+        return self._suite(_fused.suite_tqp, t, q, p, outputs)
+
+    def suite_ttdp(self, t, td, p, outputs=_fused.DEFAULT_TTDP):
+        """``fused.suite_ttdp`` for numpy arrays: returns ``{name: numpy array}``."""
+        return self._suite(_fused.suite_ttdp, t, td, p, outputs)
+
+    def ept_wet_bulb(self, t, h, p, humidity="q", ept_method="ifs", t_method="direct", potential=True):
+        """``fused.ept_wet_bulb`` for numpy arrays: returns ``(ept, wet_bulb)`` as numpy arrays."""
+        return _run(lambda x, y, z: _fused.ept_wet_bulb(x, y, z, humidity=humidity, ept_method=ept_method, t_method=t_method, potential=potential),
+                    (t, h, p), {}, self._dev())
+
+
+fused = _HostFused()
 thermo = _HostNamespace(_thermo, _thermo.__all__, "thermo")
 thermo.array = thermo  # the reference exposes the functions under ``thermo`` and ``thermo.array``
 wind = _HostNamespace(_wind, _wind.__all__, "wind")

@@ -769,3 +769,33 @@ def test_host_array_staged_pipeline_equals_device_path(ek):
     finally:
         host._STAGE_MIN, host._STAGE_CHUNK = old
         host.release_staging()
+
+
+def test_host_array_fused_kernels(ek):
+    """host.fused: the fused suites and the ept / wet-bulb kernel over numpy arrays, one pass over PCIe for all fields;
+    equal to the device call bit for bit, direct and staged pipelines."""
+    from ek_thermo import fused, host
+
+    inputs = random_inputs(N_RANDOM, seed=13)
+    t, td, q, p = (np.ascontiguousarray(inputs[k]) for k in ("t", "td", "q", "p"))
+    d = {k: torch.from_numpy(v).to(DEV) for k, v in (("t", t), ("td", td), ("q", q), ("p", p))}
+    old = (host._STAGE_MIN, host._STAGE_CHUNK)
+    try:
+        for stage_min in (old[0], 20_000):
+            host._STAGE_MIN, host._STAGE_CHUNK = stage_min, 10_000
+            host.release_staging()
+            got = host.fused.suite_tqp(t, q, p, outputs=("theta", "rh", "td", "thetav"))
+            want = fused.suite_tqp(d["t"], d["q"], d["p"], outputs=("theta", "rh", "td", "thetav"))
+            assert list(got) == ["theta", "rh", "td", "thetav"]
+            for k in got:
+                assert np.array_equal(got[k], want[k].cpu().numpy(), equal_nan=True), k
+            got = host.fused.suite_ttdp(t, td, p)
+            want = fused.suite_ttdp(d["t"], d["td"], d["p"])
+            for k in want:
+                assert np.array_equal(got[k], want[k].cpu().numpy(), equal_nan=True), k
+            ge, gw = host.fused.ept_wet_bulb(t, q, p, t_method="bisect", potential=False)
+            we, ww = fused.ept_wet_bulb(d["t"], d["q"], d["p"], t_method="bisect", potential=False)
+            assert np.array_equal(ge, we.cpu().numpy(), equal_nan=True) and np.array_equal(gw, ww.cpu().numpy(), equal_nan=True)
+    finally:
+        host._STAGE_MIN, host._STAGE_CHUNK = old
+        host.release_staging()

@@ -50,6 +50,9 @@ def main():
         for kind, arrs in (("pageable", (t, p, q)), ("pinned in, pageable out", (tp, pp, qp))):
             dt = best(lambda: fn(*arrs))
             rows.append((f"host.thermo.{name}", kind, n / dt / 1e9, bpp * n / dt / 1e9))
+    for kind, arrs in (("pageable", (t, q, p)), ("pinned in, pageable out", (tp, qp, pp))):
+        dt = best(lambda: host.fused.suite_tqp(*arrs))
+        rows.append(("host.fused.suite_tqp (5 outputs)", kind, n / dt / 1e9, 64 * n / dt / 1e9))
     hs = hostpipe.HostSuite("cuda:0", workspace_bytes=1536 << 20, n_slots=3)
     outs = {k: hostpipe.pinned_empty(n) for k in ("theta", "es", "rh", "td", "tv")}
     dt = best(lambda: hs.suite_tqp(tp, qp, pp, outputs=tuple(outs), out=outs))
