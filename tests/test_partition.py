@@ -117,6 +117,10 @@ def test_host_array_front_end_has_no_cpu_path():
     assert host.thermo.potential_temperature.__name__ == "potential_temperature"
     with pytest.raises(ValueError):
         host.set_chunk_elements(0)
+    # what counts as an array argument: numpy arrays / scalars and nested numbers, not tuples of option strings
+    assert host._is_arraylike(np.zeros(3)) and host._is_arraylike([1.0, 2.0]) and host._is_arraylike(np.float32(1.0)) and host._is_arraylike(())
+    assert not host._is_arraylike(("theta", "rh")) and not host._is_arraylike(1.0) and not host._is_arraylike("mixed") and not host._is_arraylike(None)
+    assert callable(host.fused.suite_tqp) and callable(host.fused.ept_wet_bulb)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             host.thermo.potential_temperature(np.full(4, 280.0), np.full(4, 9.0e4))
