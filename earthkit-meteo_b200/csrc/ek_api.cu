@@ -72,9 +72,13 @@ template <typename T> int ek_suite_launch_ttdp(const ek_operand* ins, void* cons
 
 // ---- host-buffer pipeline ---------------------------------------------------------------------------
 namespace {
+// The pipeline's streams.  The destructor drains them before destroying them: on an error path earlier chunks' async
+// copies may still be reading or writing the caller's host buffers, and the caller is free to release those as soon as
+// the entry point returns.
 struct StreamSet {
     std::vector<cudaStream_t> s;
     ~StreamSet() {
+        for (auto st : s) cudaStreamSynchronize(st);
         for (auto st : s) cudaStreamDestroy(st);
     }
 };

@@ -102,7 +102,13 @@ def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False)
         mask |= 1 << k
     p_ptr = c_void_p(None)
     if want_p:
-        res["p"] = out["p"] if out is not None and "p" in out else torch.empty_like(tc)
+        if out is not None and "p" in out:
+            o = out["p"]
+            if o.dtype != dtype or o.shape != t.shape or not o.is_contiguous() or o.device != dev:
+                raise ValueError(f"suite_tq_hybrid: preallocated output 'p' must be a contiguous {dtype} tensor of shape {tuple(t.shape)}")
+            res["p"] = o
+        else:
+            res["p"] = torch.empty_like(tc)
         p_ptr = c_void_p(res["p"].data_ptr())
     if npl > 0:
         _b.call_raw("suite_tq_hybrid", dtype, dev, c_void_p(tc.data_ptr()), c_void_p(qc.data_ptr()), c_void_p(spc.data_ptr()),

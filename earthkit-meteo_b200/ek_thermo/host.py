@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import functools
 import math
+import threading
 
 import numpy as np
 import torch
@@ -28,7 +29,7 @@ from . import fused as _fused
 from . import thermo as _thermo
 from . import wind as _wind
 
-__all__ = ["thermo", "wind", "fused", "set_chunk_elements", "release_staging"]
+__all__ = ["thermo", "wind", "fused", "set_chunk_elements", "set_pinned_results", "release_staging"]
 
 _CHUNK = 1 << 25  # elements per array per chunk (256 MB of float64): bounds device memory, amortises launch latency
 _TORCH = {np.dtype("float64"): torch.float64, np.dtype("float32"): torch.float32}
@@ -134,89 +135,172 @@ def _pipeline_direct(fn, args, kwargs, put, flat, dt, n, device):
 
 # ---- staged pipeline for large pageable arrays ---------------------------------------------------------------------
 # A pageable cudaMemcpy goes through the driver's single staging buffer at 7-8 GB/s.  Here worker threads copy each
-# chunk into page-locked staging buffers (numpy releases the GIL for the copy), the copies to and from the device are
-# asynchronous on the slot's stream, and other workers copy finished chunks out of staging into the result arrays (which
-# also spreads the first-touch page faults of the fresh result arrays over several cores).  Several slots keep the three
-# stages of successive chunks overlapped.
+# input chunk into page-locked staging buffers (numpy releases the GIL for the copy) while the copies to and from the
+# device run asynchronously on the slot's stream.  The RESULT arrays are page-locked themselves (numpy views of pinned
+# torch tensors from torch's caching host allocator: the first call pays cudaHostAlloc, later calls reuse the blocks of
+# results the caller has dropped), so the D2H copy lands in the array that is returned -- no second copy of the outputs.
+# `set_pinned_results(False)` returns ordinary pageable numpy arrays instead (outputs then pass through staging too).
+#
+# Re-entrancy: every running call checks a private _StagingSet out of a free list under a lock (dask's threaded
+# scheduler and xr.apply_ufunc call these functions from several threads at once); the worker pool is shared.
 _STAGE_MIN = 1 << 22    # elements: below this the direct path is used
 _STAGE_CHUNK = 1 << 22  # elements per array and staged chunk (32 MB of float64)
 _STAGE_SLOTS = 5        # chunks in flight (measured on a 16-vCPU host, theta: 3 slots 0.83, 4 slots 0.97-1.09, 5 slots 1.15 Gpt/s)
-_STAGE_LAG = 1          # a chunk is copied out of staging this many chunks after it was issued
+_STAGE_LAG = 1          # (pageable results) a chunk is copied out of staging this many chunks after it was issued
 _STAGE_WORKERS = 12     # upper bound; never more than the CPUs this process may run on
+_PINNED_RESULTS = True
 _pool = None
-_staging = {}  # (dtype, slot, role, k) -> page-locked tensor of _STAGE_CHUNK elements
+_lock = threading.Lock()
+_free_sets = []   # _StagingSet objects no call is using
+_generation = 0   # bumped by release_staging(): sets of an older generation are dropped when their call returns
+
+
+class _StagingSet:
+    """The page-locked staging buffers of ONE running call: (dtype, slot, role, k) -> pinned tensor of _STAGE_CHUNK elements."""
+
+    def __init__(self, generation):
+        self.generation = generation
+        self.bufs = {}
+
+    def buf(self, dt, slot, role, k):
+        key = (dt, slot, role, k)
+        t = self.bufs.get(key)
+        if t is None or t.numel() < _STAGE_CHUNK:
+            t = self.bufs[key] = torch.empty(_STAGE_CHUNK, dtype=_TORCH[dt], pin_memory=True)
+        return t
+
+
+def _checkout():
+    with _lock:
+        while _free_sets:
+            s = _free_sets.pop()
+            if s.generation == _generation:
+                return s
+        return _StagingSet(_generation)
+
+
+def _checkin(s):
+    with _lock:
+        if s.generation == _generation:
+            _free_sets.append(s)
 
 
 def _workers():
     global _pool
-    if _pool is None:
-        import os
-        from concurrent.futures import ThreadPoolExecutor
+    with _lock:
+        if _pool is None:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
 
-        _pool = ThreadPoolExecutor(max_workers=max(2, min(_STAGE_WORKERS, len(os.sched_getaffinity(0)))), thread_name_prefix="ek_host")
-    return _pool
+            _pool = ThreadPoolExecutor(max_workers=max(2, min(_STAGE_WORKERS, len(os.sched_getaffinity(0)))), thread_name_prefix="ek_host")
+        return _pool
 
 
-def _stage_buf(dt, slot, role, k):
-    key = (dt, slot, role, k)
-    t = _staging.get(key)
-    if t is None:
-        t = _staging[key] = torch.empty(_STAGE_CHUNK, dtype=_TORCH[dt], pin_memory=True)
-    return t
+def set_pinned_results(flag):
+    """Large results as page-locked numpy arrays (default) or ordinary pageable ones.  Returns the previous setting."""
+    global _PINNED_RESULTS
+    old = _PINNED_RESULTS
+    _PINNED_RESULTS = bool(flag)
+    return old
 
 
 def release_staging():
-    """Free the page-locked staging buffers of the host pipeline (they are kept between calls)."""
-    _staging.clear()
+    """Free the page-locked staging buffers of the host pipeline (they are kept between calls).  Safe while other threads
+    are inside a call: their sets are private and are dropped, not reused, when those calls return."""
+    global _generation
+    with _lock:
+        _generation += 1
+        _free_sets.clear()
+    empty = getattr(torch._C, "_host_emptyCache", None)  # hand cached page-locked blocks back to the OS where torch can
+    if empty is not None:
+        empty()
+
+
+def _result_array(n, dt):
+    if _PINNED_RESULTS:
+        return torch.empty(n, dtype=_TORCH[dt], pin_memory=True).numpy()  # the numpy view keeps the pinned tensor alive
+    return np.empty(n, dt)
 
 
 def _pipeline_staged(fn, args, kwargs, put, flat, dt, n, device):
+    st_set = _checkout()
+    try:
+        return _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device)
+    finally:
+        torch.cuda.synchronize(device)  # nothing of this call may still read or write the set's buffers (error paths too)
+        _checkin(st_set)
+
+
+def _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device):
     pool = _workers()
+    S = _STAGE_SLOTS
     pinned = [torch.from_numpy(a[:1]).is_pinned() for _, a in flat]  # the caller's own page-locked arrays skip staging
-    streams = [torch.cuda.Stream(device=device) for _ in range(_STAGE_SLOTS)]
-    events = [torch.cuda.Event() for _ in range(_STAGE_SLOTS)]
-    pending = [[] for _ in range(_STAGE_SLOTS)]  # copy-out futures of the chunk that used the slot last
-    ranges = [None] * _STAGE_SLOTS
+    streams = [torch.cuda.Stream(device=device) for _ in range(S)]
+    h2d_done = [None] * S  # event: the slot's input staging buffers have been read by the device
+    events = [torch.cuda.Event() for _ in range(S)]
+    pending = [[] for _ in range(S)]  # (pageable results) copy-out futures of the chunk that used the slot last
+    ranges = [None] * S
     outs = None
+    out_pinned = False
     many = False
     nres = 0
+    nchunks = -(-n // _STAGE_CHUNK)
+
+    def fill(ci):
+        """Worker threads copy chunk ci of every pageable input into the slot's staging buffers."""
+        slot = ci % S
+        b = ci * _STAGE_CHUNK
+        e = min(n, b + _STAGE_CHUNK)
+        if h2d_done[slot] is not None:
+            h2d_done[slot].synchronize()
+        return [pool.submit(np.copyto, st_set.buf(dt, slot, "in", k).numpy()[: e - b], a[b:e]) for k, (_, a) in enumerate(flat) if not pinned[k]]
 
     def copy_out(slot):
         b, e = ranges[slot]
         events[slot].synchronize()
-        pending[slot] = [pool.submit(np.copyto, outs[j][b:e], _stage_buf(dt, slot, "out", j).numpy()[: e - b]) for j in range(nres)]
+        pending[slot] = [pool.submit(np.copyto, outs[j][b:e], st_set.buf(dt, slot, "out", j).numpy()[: e - b]) for j in range(nres)]
 
-    for ci, b in enumerate(range(0, n, _STAGE_CHUNK)):
+    futs = fill(0)
+    for ci in range(nchunks):
+        b = ci * _STAGE_CHUNK
         e = min(n, b + _STAGE_CHUNK)
         m = e - b
-        slot = ci % _STAGE_SLOTS
-        for f in pending[slot]:
-            f.result()  # the slot's staging buffers are free again
-        pending[slot] = []
-        futs = [pool.submit(np.copyto, _stage_buf(dt, slot, "in", k).numpy()[:m], a[b:e]) for k, (_, a) in enumerate(flat) if not pinned[k]]
+        slot = ci % S
+        nxt = fill(ci + 1) if ci + 1 < nchunks else []  # the next chunk is staged while this one is issued
         for f in futs:
             f.result()
+        for f in pending[slot]:
+            f.result()  # (pageable results) the slot's output staging buffers are free again
+        pending[slot] = []
         with torch.cuda.stream(streams[slot]):
             for k, (s, a) in enumerate(flat):
-                src = torch.from_numpy(a[b:e]) if pinned[k] else _stage_buf(dt, slot, "in", k)[:m]
+                src = torch.from_numpy(a[b:e]) if pinned[k] else st_set.buf(dt, slot, "in", k)[:m]
                 put(s, src.to(device, non_blocking=True))
+            h2d_done[slot] = torch.cuda.Event()
+            h2d_done[slot].record()
             res = fn(*args, **kwargs)
             many = isinstance(res, tuple)
             res = res if many else (res,)
             if outs is None:
                 nres = len(res)
-                outs = [np.empty(n, dt) for _ in res]
+                out_pinned = _PINNED_RESULTS
+                outs = [_result_array(n, dt) for _ in res]
             for j, r in enumerate(res):
-                _stage_buf(dt, slot, "out", j)[:m].copy_(r.reshape(-1), non_blocking=True)
+                dst = torch.from_numpy(outs[j][b:e]) if out_pinned else st_set.buf(dt, slot, "out", j)[:m]
+                dst.copy_(r.reshape(-1), non_blocking=True)
             events[slot].record()
         ranges[slot] = (b, e)
-        if ci >= _STAGE_LAG:  # an earlier chunk has had the staging time of the chunks after it to finish on the device
-            copy_out((ci - _STAGE_LAG) % _STAGE_SLOTS)
-    for k in range(max(0, ci - _STAGE_LAG + 1), ci + 1):
-        copy_out(k % _STAGE_SLOTS)
-    for p in pending:
-        for f in p:
-            f.result()
+        futs = nxt
+        if not out_pinned and ci >= _STAGE_LAG:  # an earlier chunk has had the staging time of the chunks after it to finish
+            copy_out((ci - _STAGE_LAG) % S)
+    if not out_pinned:
+        for k in range(max(0, nchunks - _STAGE_LAG), nchunks):
+            copy_out(k % S)
+        for p in pending:
+            for f in p:
+                f.result()
+    for st in streams:
+        st.synchronize()
     return outs, many
 
 

@@ -16,6 +16,37 @@ from . import _backend as _b
 _OUTPUTS = ("full", "half", "alpha", "delta")
 
 
+def _dtype_of(x):
+    """The dtype an argument contributes to numpy-style promotion: tensors and numpy arrays their own, a Python list /
+    tuple float64 (``xp.asarray([...])`` in the reference makes a float64 array, V:630-631), a Python number nothing
+    (numpy-2 weak scalars)."""
+    if x is None or isinstance(x, (int, float)):
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.dtype
+    dt = getattr(x, "dtype", None)
+    if dt is not None:
+        try:
+            return getattr(torch, str(dt))
+        except (AttributeError, TypeError):
+            return torch.float64
+    return torch.float64
+
+
+def _working_dtype(*xs):
+    """float64 / float32 by the reference's (numpy) promotion over every array argument: a float64 operand among float32
+    ones promotes the computation, it is never cast down."""
+    dtype = None
+    for x in xs:
+        d = _dtype_of(x)
+        if d is None:
+            continue
+        if not d.is_floating_point:
+            d = torch.float64
+        dtype = d if dtype is None else torch.promote_types(dtype, d)
+    return torch.float32 if dtype in (torch.float32, torch.float16, torch.bfloat16) else torch.float64
+
+
 def _coeff_tensors(A, B, dtype, device):
     a = torch.as_tensor(A, dtype=dtype, device=device).contiguous()
     b = torch.as_tensor(B, dtype=dtype, device=device).contiguous()
@@ -40,7 +71,8 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
 
     ``sp`` is a torch CUDA tensor (float64 / float32) of any shape; ``A`` / ``B`` are array-likes with one value per
     half-level.  Returns a tensor or a tuple of tensors shaped ``(levels,) + sp.shape`` (vertical axis moved to
-    ``vertical_axis``), in the dtype of ``sp``.
+    ``vertical_axis``).  dtype as in the reference: the numpy promotion of ``sp``, ``A`` and ``B`` (Python lists count as
+    float64); ``alpha`` / ``delta`` are always float64 arrays (V:672,686).
     """
     if isinstance(output, str):
         output = (output,)
@@ -54,7 +86,7 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
     if not isinstance(sp, torch.Tensor):
         raise TypeError("ek_thermo.vertical: sp must be a torch CUDA tensor (no CPU path; use earthkit.meteo.vertical for host arrays)")
     dev = _b._check_device([sp])
-    dtype = sp.dtype if sp.dtype in (torch.float64, torch.float32) else torch.float64
+    dtype = _working_dtype(sp, A, B)  # V:630-663: A + B * sp promotes as numpy does
     spc = sp.to(dtype).contiguous()
     a, b = _coeff_tensors(A, B, dtype, dev)
     nhalf = a.numel()
@@ -87,6 +119,9 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
                     c_void_p(spc.data_ptr()), c_int64(npl), c_void_p(rows_f.data_ptr()), c_int(len(full_rows)), c_void_p(rows_h.data_ptr()),
                     c_int(len(half_rows)), c_int(top_k), c_int(top_toa), c_double(math.log(2.0) if alpha_top == "ifs" else 1.0),
                     ptr("full"), ptr("half"), ptr("delta"), ptr("alpha"))
+    for name in ("alpha", "delta"):  # the reference allocates these with xp.zeros(...), i.e. always float64 (V:672,686):
+        if name in res and dtype != torch.float64:  # float32 values, stored in a float64 array
+            res[name] = res[name].to(torch.float64)
     outs = [res[o] for o in output]
     if vertical_axis != 0 and outs[0].dim() > 1:  # V:731-733
         outs = [r.movedim(0, vertical_axis) for r in outs]
@@ -106,7 +141,7 @@ def _column_kernel(t, q, mode, vertical_axis, sp=None, A=None, B=None, alpha_top
             raise TypeError("ek_thermo.vertical: t and q must be torch CUDA tensors (no CPU path)")
     tensors = [x for x in (t, q, sp, alpha, delta, zs) if isinstance(x, torch.Tensor)]
     dev = _b._check_device(tensors)
-    dtype = t.dtype if t.dtype in (torch.float64, torch.float32) else torch.float64
+    dtype = _working_dtype(t, q, sp, alpha, delta, zs, A, B)  # numpy promotion over every array argument, never a down-cast
     if t.shape != q.shape or t.dim() < 1:
         raise ValueError(f"t and q must have the same shape, got {tuple(t.shape)} and {tuple(q.shape)}")
     if vertical_axis != 0:  # V:878-883: work with the vertical axis first

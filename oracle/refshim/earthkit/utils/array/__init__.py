@@ -7,7 +7,8 @@ earthkit-utils (pyproject.toml:33 of the reference; not vendored, not installabl
 (call sites: thermo/array/thermo.py:13,192,229,412,464,826,1048,1056,1082;
 thermo/array/es_comp.py:12,73,100,128).  This module provides exactly that for numpy so that
 ``/root/reference/src`` imports unmodified in this container when golden vectors are generated
-(tests/golden/make_golden.py) and when the oracle is pinned (oracle/pin_against_reference.py).
+and the oracle is pinned against it (both by tests/golden/make_golden.py), and when ``oracle/build_ref.py``
+installs the reference into ``oracle/_ref`` for the CPU arm of bench.py.
 It is never imported by the product package.
 """
 import numpy as _np

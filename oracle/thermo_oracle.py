@@ -4,7 +4,7 @@ A numpy restatement of the algorithm in the reference's
 ``src/earthkit/meteo/thermo/array/thermo.py`` (T), ``.../thermo/array/es_comp.py`` (E) and
 ``src/earthkit/meteo/constants/constants.py`` (C).  Every function cites the reference lines it
 follows and keeps the reference's *operation order* so that, on numpy float64, results are
-bit-identical to the reference (pinned: ``oracle/pin_against_reference.py`` compares this file
+bit-identical to the reference (pinned: ``tests/golden/make_golden.py`` compares this file
 with the live reference on seeded inputs and with the reference's golden CSVs; the outcome is
 recorded in tests/golden/PINNING.json and re-checked by tests/test_oracle_golden.py against the
 committed fixtures).

@@ -771,6 +771,62 @@ def test_host_array_staged_pipeline_equals_device_path(ek):
         host.release_staging()
 
 
+def test_host_array_pipeline_is_reentrant(ek):
+    """dask's threaded scheduler and xr.apply_ufunc call the host functions from several threads at once: every running
+    call owns its staging buffers (checked out under a lock), so concurrent calls -- and a release_staging() in the middle
+    of them -- return the same bits as the device path.  Both result flavours (page-locked and pageable arrays)."""
+    import threading
+
+    from ek_thermo import host
+
+    inputs = random_inputs(N_RANDOM, seed=21)
+    t, td, q, p = (np.ascontiguousarray(inputs[k]) for k in ("t", "td", "q", "p"))
+    d = {k: torch.from_numpy(v).to(DEV) for k, v in (("t", t), ("td", td), ("q", q), ("p", p))}
+    want = {
+        "theta": ek.thermo.potential_temperature(d["t"], d["p"]).cpu().numpy(),
+        "rh": ek.thermo.relative_humidity_from_specific_humidity(d["t"], d["q"], d["p"]).cpu().numpy(),
+        "td": ek.thermo.dewpoint_from_specific_humidity(d["q"], d["p"]).cpu().numpy(),
+        "ept": ek.thermo.ept_from_dewpoint(d["t"], d["td"], d["p"]).cpu().numpy(),
+    }
+    calls = {
+        "theta": lambda: host.thermo.potential_temperature(t, p),
+        "rh": lambda: host.thermo.relative_humidity_from_specific_humidity(t, q, p),
+        "td": lambda: host.thermo.dewpoint_from_specific_humidity(q, p),
+        "ept": lambda: host.thermo.ept_from_dewpoint(t, td, p),
+    }
+    old = (host._STAGE_MIN, host._STAGE_CHUNK)
+    host._STAGE_MIN, host._STAGE_CHUNK = 20_000, 5_000
+    host.release_staging()
+    bad = []
+
+    def worker(name, rounds):
+        try:
+            for r in range(rounds):
+                got = calls[name]()
+                if not np.array_equal(got, want[name], equal_nan=True):
+                    bad.append((name, r))
+                if name == "td" and r == 2:
+                    host.release_staging()  # while the other threads are inside their calls
+        except Exception as exc:  # noqa: BLE001 -- reported through `bad`
+            bad.append((name, repr(exc)))
+
+    try:
+        for pinned_results in (True, False):
+            prev = host.set_pinned_results(pinned_results)
+            try:
+                threads = [threading.Thread(target=worker, args=(name, 6)) for name in calls for _ in range(2)]
+                for th in threads:
+                    th.start()
+                for th in threads:
+                    th.join()
+            finally:
+                host.set_pinned_results(prev)
+            assert not bad, bad
+    finally:
+        host._STAGE_MIN, host._STAGE_CHUNK = old
+        host.release_staging()
+
+
 def test_host_array_fused_kernels(ek):
     """host.fused: the fused suites and the ept / wet-bulb kernel over numpy arrays, one pass over PCIe for all fields;
     equal to the device call bit for bit, direct and staged pipelines."""
