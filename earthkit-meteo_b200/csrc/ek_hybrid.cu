@@ -455,12 +455,15 @@ EK_API(geopotential_on_hybrid_levels,
         double alpha_top, const void* alpha, const void* delta, const void* zs, int mode, void* out, void* stream),
        (t, q, nlev, npl, sp, A, B, nhalf, top_toa, alpha_top, alpha, delta, zs, mode, out, stream))
 
-template <template <uint32_t> class OpM, template <uint32_t> class OpME, typename T>
+template <template <uint32_t, int> class OpM, template <uint32_t, int> class OpME, typename T>
 static int suite_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs,
-                        uint32_t out_mask, void* p_out, void* stream) {
+                        uint32_t out_mask, int ept_method, void* p_out, void* stream) {
     const char* what = "suite_tq_hybrid";
     if (!t || !q || !sp || !A || !B || nlev < 1 || npl < 0) return set_error(EK_ERR_ARG, "%s: bad arguments", what);
     if (out_mask >= (1u << S_NSLOTS) || (out_mask == 0 && !p_out)) return set_error(EK_ERR_ARG, "%s: out_mask=0x%x selects no output", what, out_mask);
+    constexpr uint32_t EPT = (1u << S_EPT) | (1u << S_WBPT);
+    if (!(out_mask & EPT)) ept_method = EK_EPT_IFS;
+    if (ept_method < EK_EPT_IFS || ept_method > EK_EPT_BOLTON39) return set_error(EK_ERR_ENUM, "%s: invalid ept method id %d", what, ept_method);
     SuiteHybridArgs g{t, q, sp, A, B, {}, p_out, nlev, npl, 2};
     bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(p_out);
     for (int k = 0; k < S_NSLOTS; ++k) {
@@ -478,17 +481,23 @@ static int suite_hybrid(const void* t, const void* q, const void* sp, const void
     Params P;
     P.out_mask = out_mask;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define EK_LAUNCH_SH(M)                                                                          \
-    do {                                                                                         \
-        if (vec)                                                                                 \
-            launch_kernel<&suite_hybrid_kernel<OpM<M>, OpME<M>, T, true>, T>(blocks, st, g, P);  \
-        else                                                                                     \
-            launch_kernel<&suite_hybrid_kernel<OpM<M>, OpME<M>, T, false>, T>(blocks, st, g, P); \
+#define EK_LAUNCH_SH(M, EM)                                                                              \
+    do {                                                                                                 \
+        if (vec)                                                                                         \
+            launch_kernel<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, true>, T>(blocks, st, g, P);  \
+        else                                                                                             \
+            launch_kernel<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, false>, T>(blocks, st, g, P); \
     } while (0)
-    if (out_mask == 0x1F)
-        EK_LAUNCH_SH(0x1F);
+    if (ept_method == EK_EPT_BOLTON35)
+        EK_LAUNCH_SH(0, EPT_BOLTON35);
+    else if (ept_method == EK_EPT_BOLTON39)
+        EK_LAUNCH_SH(0, EPT_BOLTON39);
+    else if (out_mask == 0x1F)
+        EK_LAUNCH_SH(0x1F, EPT_IFS);
+    else if (out_mask == 0x31F)
+        EK_LAUNCH_SH(0x31F, EPT_IFS);
     else
-        EK_LAUNCH_SH(0);
+        EK_LAUNCH_SH(0, EPT_IFS);
 #undef EK_LAUNCH_SH
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
@@ -498,10 +507,19 @@ static int suite_hybrid(const void* t, const void* q, const void* sp, const void
 
 template <typename T>
 static int impl_suite_tq_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,
-                                void* const* outs, uint32_t out_mask, void* p_out, void* stream) {
-    return suite_hybrid<EK_OPS(OpSuiteTQPm), T>(t, q, sp, A, B, nlev, npl, outs, out_mask, p_out, stream);
+                                void* const* outs, uint32_t out_mask, int ept_method, void* p_out, void* stream) {
+    return suite_hybrid<EK_OPS(OpSuiteTQPm), T>(t, q, sp, A, B, nlev, npl, outs, out_mask, ept_method, p_out, stream);
 }
 EK_API(suite_tq_hybrid,
        (const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs, uint32_t out_mask,
-        void* p_out, void* stream),
-       (t, q, sp, A, B, nlev, npl, outs, out_mask, p_out, stream))
+        int ept_method, void* p_out, void* stream),
+       (t, q, sp, A, B, nlev, npl, outs, out_mask, ept_method, p_out, stream))
+
+// used by the host-buffer pipeline in ek_api.cu
+template <typename T>
+int ek_suite_launch_hybrid(const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl, void* const* outs,
+                           uint32_t out_mask, int ept_method, void* stream) {
+    return suite_hybrid<EK_OPS(OpSuiteTQPm), T>(t, q, sp, A, B, nlev, npl, outs, out_mask, ept_method, nullptr, stream);
+}
+template int ek_suite_launch_hybrid<double>(const void*, const void*, const void*, const void*, const void*, int, int64_t, void* const*, uint32_t, int, void*);
+template int ek_suite_launch_hybrid<float>(const void*, const void*, const void*, const void*, const void*, int, int64_t, void* const*, uint32_t, int, void*);

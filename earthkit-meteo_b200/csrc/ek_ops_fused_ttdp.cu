@@ -2,14 +2,15 @@
 #include "ek_ops_fused_impl.cuh"
 
 template <typename T>
-static int impl_suite_ttdp(ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t m, int64_t n, void* stream) {
-    return suite<EK_OPS(OpSuiteTTdPm), T>("suite_ttdp", t, td, p, outs, m, n, stream);
+static int impl_suite_ttdp(ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t m, int ept_method, int64_t n, void* stream) {
+    return suite<EK_OPS(OpSuiteTTdPm), T>("suite_ttdp", t, td, p, outs, m, ept_method, n, stream);
 }
-EK_API(suite_ttdp, (ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t m, int64_t n, void* stream), (t, td, p, outs, m, n, stream))
+EK_API(suite_ttdp, (ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t m, int ept_method, int64_t n, void* stream),
+       (t, td, p, outs, m, ept_method, n, stream))
 
 // used by the host-buffer pipeline in ek_api.cu
-template <typename T> int ek_suite_launch_ttdp(const ek_operand* ins, void* const* outs, uint32_t mask, int64_t n, void* stream) {
-    return suite<EK_OPS(OpSuiteTTdPm), T>("host_suite", ins[0], ins[1], ins[2], outs, mask, n, stream);
+template <typename T> int ek_suite_launch_ttdp(const ek_operand* ins, void* const* outs, uint32_t mask, int ept_method, int64_t n, void* stream) {
+    return suite<EK_OPS(OpSuiteTTdPm), T>("host_suite", ins[0], ins[1], ins[2], outs, mask, ept_method, n, stream);
 }
-template int ek_suite_launch_ttdp<double>(const ek_operand*, void* const*, uint32_t, int64_t, void*);
-template int ek_suite_launch_ttdp<float>(const ek_operand*, void* const*, uint32_t, int64_t, void*);
+template int ek_suite_launch_ttdp<double>(const ek_operand*, void* const*, uint32_t, int, int64_t, void*);
+template int ek_suite_launch_ttdp<float>(const ek_operand*, void* const*, uint32_t, int, int64_t, void*);

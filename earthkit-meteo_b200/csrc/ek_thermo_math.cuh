@@ -205,7 +205,7 @@ struct Params {
 };
 
 // output slots of the fused suites (see ek_thermo_ops.inc)
-enum SuiteSlot : int { S_THETA = 0, S_ES = 1, S_RH = 2, S_TDQ = 3, S_TV = 4, S_W = 5, S_E = 6, S_THETAV = 7, S_NSLOTS = 8 };
+enum SuiteSlot : int { S_THETA = 0, S_ES = 1, S_RH = 2, S_TDQ = 3, S_TV = 4, S_W = 5, S_E = 6, S_THETAV = 7, S_EPT = 8, S_WBPT = 9, S_NSLOTS = 10 };
 
 }  // namespace ek
 

@@ -100,7 +100,7 @@ for _name, (_nin, _opts, _nout) in SIGNATURES.items():
 for _name in ("suite_tqp", "suite_ttdp"):
     for _sfx in ("f64", "f32"):
         _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
-        _fn.argtypes = [ek_operand] * 3 + [ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p]
+        _fn.argtypes = [ek_operand] * 3 + [ctypes.POINTER(c_void_p), c_uint32, c_int, c_int64, c_void_p]
         _fn.restype = c_int
 _c_int_p = ctypes.POINTER(c_int)
 for _sfx in ("f64", "f32"):
@@ -116,11 +116,16 @@ for _sfx in ("f64", "f32"):
                     c_int, c_void_p, c_void_p]
     _fn.restype = c_int
     _fn = getattr(_lib, f"ek_thermo_suite_tq_hybrid_{_sfx}")
-    _fn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, ctypes.POINTER(c_void_p), c_uint32, c_void_p, c_void_p]
+    _fn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, ctypes.POINTER(c_void_p), c_uint32, c_int, c_void_p,
+                    c_void_p]
     _fn.restype = c_int
 for _sfx in ("f64", "f32"):
     _fn = getattr(_lib, f"ek_thermo_host_suite_{_sfx}")
-    _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_uint32, c_int64, c_void_p, c_size_t, c_int]
+    _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_uint32, c_int, c_int64, c_void_p, c_size_t, c_int]
+    _fn.restype = c_int
+    _fn = getattr(_lib, f"ek_thermo_host_suite_tq_hybrid_{_sfx}")
+    _fn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, ctypes.POINTER(c_void_p), c_uint32, c_int, c_void_p,
+                    c_size_t, c_int]
     _fn.restype = c_int
 
 
@@ -328,10 +333,13 @@ def execute(symbol: str, args, options=(), want=None):
     return res[0] if len(res) == 1 else res
 
 
-def execute_suite(symbol: str, args, out_names, slots, out=None):
+N_SUITE_SLOTS = 10  # EK_S_NSLOTS (include/ek_thermo.h)
+
+
+def execute_suite(symbol: str, args, out_names, slots, out=None, ept_method=0):
     """Run a fused suite; `slots` are the output slot numbers wanted; returns {name: tensor}."""
     ops, keep, dtype, dev, shape, n = _prepare(args)
-    ptrs = (c_void_p * 8)()
+    ptrs = (c_void_p * N_SUITE_SLOTS)()
     mask = 0
     res = {}
     for name, k in zip(out_names, slots):
@@ -345,7 +353,7 @@ def execute_suite(symbol: str, args, out_names, slots, out=None):
         ptrs[k] = t.data_ptr()
         mask |= 1 << k
     if n > 0:
-        _call(symbol, dtype, dev, [*ops, ptrs, mask, n])
+        _call(symbol, dtype, dev, [*ops, ptrs, mask, ept_method, n])
     del keep
     return res
 
@@ -356,10 +364,22 @@ def shard_range(n: int, world: int, rank: int, align: int = 1):
     return int(b.value), int(e.value)
 
 
-def host_suite(kind: int, dtype, h_ptrs, h_out_ptrs, mask: int, n: int, workspace: torch.Tensor, n_slots: int):
+def host_suite(kind: int, dtype, h_ptrs, h_out_ptrs, mask: int, ept_method: int, n: int, workspace: torch.Tensor, n_slots: int):
     fn = getattr(_lib, f"ek_thermo_host_suite_{_SUFFIX[dtype]}")
-    outs = (c_void_p * 8)(*h_out_ptrs)
+    outs = (c_void_p * N_SUITE_SLOTS)(*h_out_ptrs)
     with torch.cuda.device(workspace.device):
+        torch.cuda.current_stream().synchronize()  # the pipeline runs on its own streams: nothing may be pending on the workspace
         _check(fn(kind, c_void_p(h_ptrs[0]), c_void_p(h_ptrs[1]), c_void_p(h_ptrs[2]), ctypes.cast(outs, ctypes.POINTER(c_void_p)),
-                  c_uint32(mask), c_int64(n), c_void_p(workspace.data_ptr()), c_size_t(workspace.numel() * workspace.element_size()),
-                  c_int(n_slots)))
+                  c_uint32(mask), c_int(ept_method), c_int64(n), c_void_p(workspace.data_ptr()),
+                  c_size_t(workspace.numel() * workspace.element_size()), c_int(n_slots)))
+
+
+def host_suite_tq_hybrid(dtype, h_t, h_q, h_sp, h_a, h_b, nlev: int, npl: int, h_out_ptrs, mask: int, ept_method: int, workspace: torch.Tensor,
+                         n_slots: int):
+    fn = getattr(_lib, f"ek_thermo_host_suite_tq_hybrid_{_SUFFIX[dtype]}")
+    outs = (c_void_p * N_SUITE_SLOTS)(*h_out_ptrs)
+    with torch.cuda.device(workspace.device):
+        torch.cuda.current_stream().synchronize()
+        _check(fn(c_void_p(h_t), c_void_p(h_q), c_void_p(h_sp), c_void_p(h_a), c_void_p(h_b), c_int(nlev), c_int64(npl),
+                  ctypes.cast(outs, ctypes.POINTER(c_void_p)), c_uint32(mask), c_int(ept_method), c_void_p(workspace.data_ptr()),
+                  c_size_t(workspace.numel() * workspace.element_size()), c_int(n_slots)))

@@ -19,6 +19,8 @@ SUITE_TQP_OUTPUTS = {
     "w": 5,  # mixing_ratio_from_specific_humidity(q)                    T:80-102
     "e": 6,  # vapour_pressure_from_specific_humidity(q, p)              T:105-131
     "thetav": 7,  # virtual_potential_temperature(t, q, p)               T:767-798
+    "ept": 8,  # ept_from_specific_humidity(t, q, p, method=ept_method)  T:1390-1415
+    "wbpt": 9,  # wet_bulb_potential_temperature_from_specific_humidity(t, q, p, ept_method, t_method="direct")  T:1637-1675
 }
 SUITE_TTDP_OUTPUTS = {
     "theta": 0,  # potential_temperature(t, p)
@@ -29,7 +31,15 @@ SUITE_TTDP_OUTPUTS = {
     "w": 5,  # mixing_ratio_from_dewpoint(td, p)                         T:594-626
     "e": 6,  # saturation_vapour_pressure(td, phase="water")
     "thetav": 7,  # virtual_potential_temperature(t, q(td, p), p)
+    "ept": 8,  # ept_from_dewpoint(t, td, p, method=ept_method)          T:1326-1387
+    "wbpt": 9,  # wet_bulb_potential_temperature_from_dewpoint(t, td, p, ept_method, t_method="direct")  T:1593-1634
 }
+# the single pass BASELINE.json names: "read t/q/p (or t/td/p) once and write theta, rh, td, theta_e and wbpt"
+SINGLE_PASS_TQP = ("theta", "rh", "td", "ept", "wbpt")
+SINGLE_PASS_TTDP = ("theta", "rh", "q", "ept", "wbpt")
+# ... and with the two remaining fields of the default suite: 10 arrays = 80 bytes per point in float64
+ALL7_TQP = ("theta", "es", "rh", "td", "tv", "ept", "wbpt")
+ALL7_TTDP = ("theta", "es", "rh", "q", "tv", "ept", "wbpt")
 DEFAULT_TQP = ("theta", "es", "rh", "td", "tv")
 DEFAULT_TTDP = ("theta", "es", "rh", "q", "tv")
 
@@ -44,19 +54,25 @@ def _slots(table, outputs):
         raise ValueError(f"unknown suite output {e.args[0]!r}; choose from {sorted(table)}") from None
 
 
-def suite_tqp(t, q, p, outputs=DEFAULT_TQP, out=None):
-    """One pass over (t, q, p) producing the requested fields; returns ``{name: tensor}``."""
+def _ept_id(ept_method):
+    return _EPT[ept_method]  # KeyError for an unknown method, as the reference (T:1026)
+
+
+def suite_tqp(t, q, p, outputs=DEFAULT_TQP, out=None, ept_method="ifs"):
+    """One pass over (t, q, p) producing the requested fields; returns ``{name: tensor}``.
+
+    ``ept_method`` ("ifs", "bolton35", "bolton39") is the formulation of the ``"ept"`` / ``"wbpt"`` outputs."""
     outputs = tuple(outputs)
-    return _b.execute_suite("suite_tqp", (t, q, p), outputs, _slots(SUITE_TQP_OUTPUTS, outputs), out)
+    return _b.execute_suite("suite_tqp", (t, q, p), outputs, _slots(SUITE_TQP_OUTPUTS, outputs), out, _ept_id(ept_method))
 
 
-def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None):
+def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None, ept_method="ifs"):
     """One pass over (t, td, p) producing the requested fields; returns ``{name: tensor}``."""
     outputs = tuple(outputs)
-    return _b.execute_suite("suite_ttdp", (t, td, p), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out)
+    return _b.execute_suite("suite_ttdp", (t, td, p), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out, _ept_id(ept_method))
 
 
-def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False):
+def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False, ept_method="ifs"):
     """The (t, q, p) suite on hybrid model levels with the pressure computed inside the kernel.
 
     ``t`` and ``q`` are ``[nlev, ...]`` fields, ``sp`` the surface pressure ``[...]``, ``A`` / ``B`` the ``nlev + 1``
@@ -87,9 +103,10 @@ def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False)
     if a.numel() != nlev + 1 or b.numel() != nlev + 1:
         raise ValueError(f"suite_tq_hybrid: A and B need nlev + 1 = {nlev + 1} half-level values")
     tc, qc, spc = t.contiguous(), q.contiguous(), sp.contiguous()
-    ptrs = (c_void_p * 8)()
+    ptrs = (c_void_p * _b.N_SUITE_SLOTS)()
     mask = 0
     res = {}
+    em = _ept_id(ept_method)
     for name, k in zip(outputs, slots):
         if out is not None and name in out:
             o = out[name]
@@ -113,7 +130,7 @@ def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False)
     if npl > 0:
         _b.call_raw("suite_tq_hybrid", dtype, dev, c_void_p(tc.data_ptr()), c_void_p(qc.data_ptr()), c_void_p(spc.data_ptr()),
                     c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), c_int(nlev), c_int64(npl), ctypes.cast(ptrs, ctypes.POINTER(c_void_p)),
-                    c_uint32(mask), p_ptr)
+                    c_uint32(mask), c_int(em), p_ptr)
     return res
 
 

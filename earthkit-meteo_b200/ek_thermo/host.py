@@ -333,18 +333,18 @@ class _HostFused:
     def _dev(self):
         return torch.device("cuda", torch.cuda.current_device()) if self.device is None and torch.cuda.is_available() else self.device
 
-    def _suite(self, fn, a, b, c, outputs):
+    def _suite(self, fn, a, b, c, outputs, ept_method):
         outputs = tuple(outputs)
-        res = _run(lambda x, y, z: tuple(fn(x, y, z, outputs=outputs).values()), (a, b, c), {}, self._dev())
+        res = _run(lambda x, y, z: tuple(fn(x, y, z, outputs=outputs, ept_method=ept_method).values()), (a, b, c), {}, self._dev())
         return dict(zip(outputs, res if isinstance(res, tuple) else (res,)))
 
-    def suite_tqp(self, t, q, p, outputs=_fused.DEFAULT_TQP):
+    def suite_tqp(self, t, q, p, outputs=_fused.DEFAULT_TQP, ept_method="ifs"):
         """``fused.suite_tqp`` for numpy arrays: returns ``{name: numpy array}``."""
-        return self._suite(_fused.suite_tqp, t, q, p, outputs)
+        return self._suite(_fused.suite_tqp, t, q, p, outputs, ept_method)
 
-    def suite_ttdp(self, t, td, p, outputs=_fused.DEFAULT_TTDP):
+    def suite_ttdp(self, t, td, p, outputs=_fused.DEFAULT_TTDP, ept_method="ifs"):
         """``fused.suite_ttdp`` for numpy arrays: returns ``{name: numpy array}``."""
-        return self._suite(_fused.suite_ttdp, t, td, p, outputs)
+        return self._suite(_fused.suite_ttdp, t, td, p, outputs, ept_method)
 
     def ept_wet_bulb(self, t, h, p, humidity="q", ept_method="ifs", t_method="direct", potential=True):
         """``fused.ept_wet_bulb`` for numpy arrays: returns ``(ept, wet_bulb)`` as numpy arrays."""

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EK_THERMO_VERSION 100 /* 0.1.0 */
+#define EK_THERMO_VERSION 110 /* 0.1.1: suite slots 8 (ept) / 9 (wbpt) and their ept_method argument; host pipelines for every suite */
 
 typedef struct ek_operand {
     const void* ptr; /* device pointer, or NULL for a broadcast scalar */
@@ -49,7 +49,9 @@ enum { EK_HUM_DEWPOINT = 0, EK_HUM_SPECIFIC = 1 };
 /* output slots of the fused suites (bit k of out_mask <-> outs[k]) */
 enum {
     EK_S_THETA = 0, EK_S_ES = 1, EK_S_RH = 2, EK_S_TD_OR_Q = 3, EK_S_TV = 4, EK_S_W = 5, EK_S_E = 6, EK_S_THETAV = 7,
-    EK_S_NSLOTS = 8
+    EK_S_EPT = 8,  /* ept_from_specific_humidity / ept_from_dewpoint, T:1390-1415 / T:1326-1387 */
+    EK_S_WBPT = 9, /* wet_bulb_potential_temperature_from_*, t_method="direct" (the reference's default), T:1637-1675 / T:1593-1634 */
+    EK_S_NSLOTS = 10
 };
 
 /* declares ek_thermo_<name>_f64 and ek_thermo_<name>_f32 with the same parameter list */
@@ -129,10 +131,15 @@ EK_THERMO_FN(wet_bulb_potential_temperature_from_specific_humidity, ek_operand t
 
 /* ---- fused multi-output kernels (new in this build; each output equals the reference function named
  *      at its slot, see EK_S_*) ------------------------------------------------------------------- */
-/* (t, q, p) -> any subset of {theta, es, rh, td, tv, w, e, thetav}; outs[k] may be NULL when bit k is clear */
-EK_THERMO_FN(suite_tqp, ek_operand t, ek_operand q, ek_operand p, void* const* outs, uint32_t out_mask, int64_t n, void* stream)
-/* (t, td, p) -> any subset of {theta, es, rh, q, tv, w, e, thetav} */
-EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t out_mask, int64_t n, void* stream)
+/* (t, q, p) -> any subset of {theta, es, rh, td, tv, w, e, thetav, ept, wbpt}; outs has EK_S_NSLOTS entries, outs[k] may be
+ * NULL when bit k is clear.  ept_method (EK_EPT_*) is the formulation of slots 8 / 9 and is ignored when neither is asked
+ * for.  One launch with mask 0x30D is the single pass "read t/q/p once, write theta, rh, td, theta_e, theta_w"; the chain it
+ * replaces in the reference is T:1637-1675 -> T:1390-1415 -> T:1031-1040 -> T:702-735 + T:801-829. */
+EK_THERMO_FN(suite_tqp, ek_operand t, ek_operand q, ek_operand p, void* const* outs, uint32_t out_mask, int ept_method, int64_t n,
+             void* stream)
+/* (t, td, p) -> any subset of {theta, es, rh, q, tv, w, e, thetav, ept, wbpt} */
+EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const* outs, uint32_t out_mask, int ept_method, int64_t n,
+             void* stream)
 /* (t, h, p) -> ept and/or the wet-bulb (potential) temperature in one pass.  h is td or q (humidity_kind),
  * at_p0 = 1 gives the wet-bulb POTENTIAL temperature; either output pointer may be NULL (but not both);
  * t_method EK_TM_NONE computes ept only */
@@ -175,15 +182,22 @@ EK_THERMO_FN(geopotential_on_hybrid_levels, const void* t, const void* q, int nl
 /* the (t, q, p) suite with p = full-level pressure computed in registers from sp and A/B (nlev + 1 coefficients each);
  * t, q and every output are [nlev, npl]; p_out (optional) receives the pressure itself */
 EK_THERMO_FN(suite_tq_hybrid, const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,
-             void* const* outs, uint32_t out_mask, void* p_out, void* stream)
+             void* const* outs, uint32_t out_mask, int ept_method, void* p_out, void* stream)
 
-/* ---- host-buffer pipeline: the same suite kernel fed from HOST arrays ---------------------------------
- * Streams n points through the GPU in chunks: H2D copy, kernel and D2H copy of successive chunks overlap on
+/* ---- host-buffer pipelines: the same suite kernels fed from HOST arrays ------------------------------
+ * Stream n points through the GPU in chunks: H2D copy, kernel and D2H copy of successive chunks overlap on
  * `n_slots` internal streams.  Host buffers should be page-locked for full PCIe speed.  `workspace` is a
- * caller-owned DEVICE buffer of workspace_bytes; chunk size = workspace_bytes / (n_slots * (3 + popcount(mask)) * sizeof(T)).
- * Blocks until every output byte is in host memory.  kind: 0 = suite_tqp, 1 = suite_ttdp. */
+ * caller-owned DEVICE buffer of workspace_bytes with no work pending on it; chunk size = workspace_bytes /
+ * (n_slots * (3 + popcount(mask)) * sizeof(T)).  Block until every output byte is in host memory (also on error:
+ * the pipeline's streams are drained before the call returns).  kind: 0 = suite_tqp, 1 = suite_ttdp; out_mask,
+ * ept_method as for the suites (slots 8 / 9 included, so the ept / wet-bulb workload has a host path too). */
 EK_THERMO_FN(host_suite, int kind, const void* h_a, const void* h_b, const void* h_c, void* const* h_outs, uint32_t out_mask,
-             int64_t n, void* workspace, size_t workspace_bytes, int n_slots)
+             int ept_method, int64_t n, void* workspace, size_t workspace_bytes, int n_slots)
+/* suite_tq_hybrid from HOST arrays: h_t, h_q and every output [nlev, npl], h_sp [npl], h_A / h_B nlev + 1 half-level
+ * coefficients.  The pressure field exists on neither side of PCIe (16 + 8/nlev instead of 24 bytes per point travel
+ * to the device).  Chunks are column ranges of all levels, moved as 2-D copies. */
+EK_THERMO_FN(host_suite_tq_hybrid, const void* h_t, const void* h_q, const void* h_sp, const void* h_A, const void* h_B, int nlev,
+             int64_t npl, void* const* h_outs, uint32_t out_mask, int ept_method, void* workspace, size_t workspace_bytes, int n_slots)
 
 #ifdef __cplusplus
 }

@@ -637,8 +637,9 @@ def wet_bulb_potential_temperature_from_specific_humidity(t, q, p, ept_method="i
 
 
 # --- the fused suites of the new build, stated as compositions of the reference functions -----
-def suite_tqp(t, q, p):
-    """What the fused (t,q,p) kernel must equal, output by output (BASELINE.json configs[1])."""
+def suite_tqp(t, q, p, ept_method="ifs"):
+    """What the fused (t,q,p) kernel must equal, output by output (BASELINE.json configs[1]; "ept" / "wbpt" are the
+    configs[2] pair: the reference chain T:1637-1675 -> T:1390-1415 -> T:1031-1040 with its default t_method)."""
     return {
         "theta": potential_temperature(t, p),
         "es": saturation_vapour_pressure(t),
@@ -648,10 +649,12 @@ def suite_tqp(t, q, p):
         "w": mixing_ratio_from_specific_humidity(q),
         "e": vapour_pressure_from_specific_humidity(q, p),
         "thetav": virtual_potential_temperature(t, q, p),
+        "ept": ept_from_specific_humidity(t, q, p, method=ept_method),
+        "wbpt": wet_bulb_potential_temperature_from_specific_humidity(t, q, p, ept_method=ept_method, t_method="direct"),
     }
 
 
-def suite_ttdp(t, td, p):
+def suite_ttdp(t, td, p, ept_method="ifs"):
     """What the fused (t,td,p) kernel must equal, output by output."""
     q = specific_humidity_from_dewpoint(td, p)
     return {
@@ -663,6 +666,8 @@ def suite_ttdp(t, td, p):
         "w": mixing_ratio_from_dewpoint(td, p),
         "e": saturation_vapour_pressure(td, phase="water"),
         "thetav": virtual_potential_temperature(t, q, p),
+        "ept": ept_from_dewpoint(t, td, p, method=ept_method),
+        "wbpt": wet_bulb_potential_temperature_from_dewpoint(t, td, p, ept_method=ept_method, t_method="direct"),
     }
 
 

@@ -92,9 +92,21 @@ extern "C" int hostmath_run(const char* op, int f32, const void* const* ins, con
     EK_CASE("wind_polar_to_xy", OpPolarToXy)
     EK_CASE("w_from_omega", OpWFromOmega)
     EK_CASE("coriolis", OpCoriolis)
-    EK_CASE("suite_tqp", OpSuiteTQP)
-    EK_CASE("suite_ttdp", OpSuiteTTdP)
 #undef EK_CASE
+    if (s == "suite_tqp" || s == "suite_ttdp") {  // generic (run-time mask) instantiation, per ept formulation
+        const bool q = s == "suite_tqp";
+        switch (m) {
+            case EPT_IFS: return q ? both<OpSuiteTQPm<0, EPT_IFS>>(f32, ins, scalars, outs, n, P) : both<OpSuiteTTdPm<0, EPT_IFS>>(f32, ins, scalars, outs, n, P);
+            case EPT_BOLTON35: return q ? both<OpSuiteTQPm<0, EPT_BOLTON35>>(f32, ins, scalars, outs, n, P) : both<OpSuiteTTdPm<0, EPT_BOLTON35>>(f32, ins, scalars, outs, n, P);
+            case EPT_BOLTON39: return q ? both<OpSuiteTQPm<0, EPT_BOLTON39>>(f32, ins, scalars, outs, n, P) : both<OpSuiteTTdPm<0, EPT_BOLTON39>>(f32, ins, scalars, outs, n, P);
+        }
+        return -2;
+    }
+    // the compile-time-mask instantiations the library ships (0x31F: the seven-output single pass, 0x30D: theta, rh, td|q, ept, wbpt)
+    if (s == "suite_tqp_31f") return both<OpSuiteTQPm<0x31F, EPT_IFS>>(f32, ins, scalars, outs, n, P);
+    if (s == "suite_ttdp_31f") return both<OpSuiteTTdPm<0x31F, EPT_IFS>>(f32, ins, scalars, outs, n, P);
+    if (s == "suite_tqp_30d") return both<OpSuiteTQPm<0x30D, EPT_IFS>>(f32, ins, scalars, outs, n, P);
+    if (s == "suite_ttdp_30d") return both<OpSuiteTTdPm<0x30D, EPT_IFS>>(f32, ins, scalars, outs, n, P);
     if (s == "hyb_full" || s == "hyb_delta_alpha") {  // hybrid-level formulas (ek_thermo_formulas.inc), per point
         for (int64_t i = 0; i < n; ++i) {
             auto in = [&](int k) { return f32 ? (double)static_cast<const float*>(ins[k])[i] : static_cast<const double*>(ins[k])[i]; };

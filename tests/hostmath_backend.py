@@ -56,10 +56,11 @@ def fake_call(symbol, dtype, device, c_args):
     from ek_thermo import _backend as b
 
     if symbol in ("suite_tqp", "suite_ttdp"):
-        operands, (outs, mask, n) = c_args[:3], c_args[3:]
+        operands, (outs, mask, em, n) = c_args[:3], c_args[3:]
         mask = _val(mask)
-        o = [outs[k] if (mask >> k) & 1 else None for k in range(8)]
-        return _run(symbol, dtype, operands, o, _val(n), mask=mask)
+        o = [outs[k] if (mask >> k) & 1 else None for k in range(b.N_SUITE_SLOTS)]
+        op = symbol + {0x31F: "_31f", 0x30D: "_30d"}.get(mask, "") if _val(em) == 0 else symbol  # the static-mask instantiations, like the library
+        return _run(op, dtype, operands, o, _val(n), mask=mask, m=_val(em))
     nin, opt_types, nout = b.SIGNATURES[symbol]
     operands = c_args[:nin]
     opts = [_val(x) for x in c_args[nin:nin + len(opt_types)]]

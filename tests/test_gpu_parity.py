@@ -262,124 +262,7 @@ def test_fused_ept_wet_bulb_equals_separate_calls(ek, ept_method, t_method):
             torch.testing.assert_close(wb, w1, rtol=2e-9, atol=0, equal_nan=True)
 
 
-# ---- full-size properties (BASELINE.json configs[1]: O1280 x 137 levels, float64) -----------------
-def test_full_size_o1280_x137_properties(ek):
-    """At 904 156 160 points the oracle cannot run in full; check size-independent properties instead:
-    (i) the fused outputs equal the single-function kernels to 1e-14 over the whole field,
-    (ii) a strided sample of 1e6 points equals the oracle, (iii) kelvin<->celsius and theta<->t round trips."""
-    from ek_thermo import fused
-
-    n = 6599680 * 137
-    free, _ = torch.cuda.mem_get_info()
-    if free < 70e9:
-        pytest.skip("needs ~65 GB of free HBM")
-    g = torch.Generator(device=DEV).manual_seed(0)
-    t = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(200.0, 320.0, generator=g)
-    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e3, 1.05e5, generator=g)
-    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-6, 0.02, generator=g)
-    out = fused.suite_tqp(t, q, p)
-    idx = torch.arange(0, n, 887, device=DEV)  # ~1.02e6 sampled points through the numpy oracle
-    ts, qs, ps = (x[idx].cpu().numpy() for x in (t, q, p))
-    with np.errstate(all="ignore"):
-        want = oracle.suite_tqp(ts, qs, ps)
-    for name in fused.DEFAULT_TQP:
-        np.testing.assert_allclose(out[name][idx].cpu().numpy(), want[name], rtol=1e-12, equal_nan=True, err_msg=name)
-    singles = {
-        "theta": lambda: ek.thermo.potential_temperature(t, p),
-        "es": lambda: ek.thermo.saturation_vapour_pressure(t),
-        "rh": lambda: ek.thermo.relative_humidity_from_specific_humidity(t, q, p),
-        "td": lambda: ek.thermo.dewpoint_from_specific_humidity(q, p),
-        "tv": lambda: ek.thermo.virtual_temperature(t, q),
-    }
-    for name, fn in singles.items():
-        one = fn()
-        # different kernels may contract a*b+c into FMAs differently: allow a few ulps, nothing more
-        same = ((one - out[name]).abs() <= 1e-14 * one.abs()) | (torch.isnan(one) & torch.isnan(out[name]))
-        assert bool(same.all()), name
-        del one, same
-    th = out["theta"]
-    back = ek.thermo.temperature_from_potential_temperature(th, p)
-    assert float(((back - t).abs() / t).max()) < 1e-13
-    del back
-    c = ek.thermo.kelvin_to_celsius(t)
-    k2 = ek.thermo.celsius_to_kelvin(c)
-    assert float((k2 - t).abs().max()) < 1e-12
-
-
-def test_full_size_config3_ept_wbpt_properties(ek):
-    """BASELINE.json configs[2]: ept + wet-bulb potential temperature on O1280 x 137 levels (904 156 160 points),
-    float64 and float32.  Properties: a strided 5e5-point sample equals the oracle; theta_e >= theta (q >= 0);
-    theta_w <= theta_e; the fused kernel equals the two single-output entry points on a level slab."""
-    from ek_thermo import fused
-
-    n = 6599680 * 137
-    free, _ = torch.cuda.mem_get_info()
-    if free < 45e9:
-        pytest.skip("needs ~40 GB of free HBM")
-    g = torch.Generator(device=DEV).manual_seed(1)
-    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(2.0e4, 1.05e5, generator=g)
-    t = (288.15 * (p / 101325.0) ** 0.19).add_(torch.empty(n, device=DEV, dtype=torch.float64).uniform_(-10.0, 10.0, generator=g))
-    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-6, 4.0e-3, generator=g)
-    idx = torch.arange(0, n, 1801, device=DEV)
-    for dt, rtol in ((torch.float64, 1e-12), (torch.float32, 2e-5)):
-        tt, qq, pp = t.to(dt), q.to(dt), p.to(dt)
-        ept, wb = fused.ept_wet_bulb(tt, qq, pp, humidity="q", ept_method="ifs", t_method="direct", potential=True)
-        ts, qs, ps = (x[idx].cpu().numpy() for x in (tt, qq, pp))
-        with np.errstate(all="ignore"):
-            want_e = oracle.ept_from_specific_humidity(ts, qs, ps).astype(np.float64)
-            want_w = np.asarray(oracle.wet_bulb_potential_temperature_from_specific_humidity(ts, qs, ps)).astype(np.float64)
-        got_e, got_w = ept[idx].cpu().numpy().astype(np.float64), wb[idx].cpu().numpy().astype(np.float64)
-        assert np.mean(np.abs(got_e - want_e) > rtol * np.abs(want_e)) <= (0.0 if dt == torch.float64 else 0.01)
-        assert np.mean(np.abs(got_w - want_w) > 4 * rtol * np.abs(want_w)) <= (0.0 if dt == torch.float64 else 0.01)
-        theta = ek.thermo.potential_temperature(tt, pp)
-        assert bool((ept >= theta * (1 - 1e-6)).all()) and bool((wb <= ept).all())
-        del theta
-        sl = slice(0, 6599680)
-        e1 = ek.thermo.ept_from_specific_humidity(tt[sl], qq[sl], pp[sl])
-        w1 = ek.thermo.wet_bulb_potential_temperature_from_specific_humidity(tt[sl], qq[sl], pp[sl])
-        torch.testing.assert_close(ept[sl], e1, rtol=(1e-13 if dt == torch.float64 else 1e-6), atol=0)
-        torch.testing.assert_close(wb[sl], w1, rtol=(1e-12 if dt == torch.float64 else 1e-5), atol=0)
-        del ept, wb, tt, qq, pp, e1, w1
-
-
-def test_full_size_config4_ens_shard_conversions(ek):
-    """BASELINE.json configs[3]: one GPU's shard of ENS 51 x O640 x 137 (1 451 060 160 points), humidity / dewpoint
-    conversions.  Round trips through the inverse functions over the whole shard (size-independent properties),
-    a sampled comparison with the oracle, and the shard edges produced by the partitioner."""
-    from ek_thermo import fused, partition
-
-    n_total, slab = 51 * 137 * 1661440, 1661440
-    b, e = partition.shard_range(n_total, 8, 3, align=slab)
-    n = e - b
-    assert n in (873 * slab, 874 * slab)
-    free, _ = torch.cuda.mem_get_info()
-    if free < 75e9:
-        pytest.skip("needs ~70 GB of free HBM")
-    g = torch.Generator(device=DEV).manual_seed(2)
-    p = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(3.0e4, 1.05e5, generator=g)
-    t = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(235.0, 310.0, generator=g)
-    q = torch.empty(n, device=DEV, dtype=torch.float64).uniform_(1.0e-5, 2.0e-3, generator=g)
-    th = ek.thermo
-    td = th.dewpoint_from_specific_humidity(q, p)
-    q2 = th.specific_humidity_from_dewpoint(td, p)
-    assert float(((q2 - q).abs() / q).max()) < 1e-11  # q -> td -> q
-    del q2
-    r = th.relative_humidity_from_dewpoint(t, td)
-    td2 = th.dewpoint_from_relative_humidity(t, r)
-    assert float(((td2 - td).abs() / td).max()) < 1e-12  # td -> r -> td
-    del td2, r
-    w = th.mixing_ratio_from_specific_humidity(q)
-    q3 = th.specific_humidity_from_mixing_ratio(w)
-    assert float(((q3 - q).abs() / q).max()) < 1e-14
-    del q3
-    out = fused.suite_tqp(t, q, p, outputs=("rh", "td", "w"))
-    torch.testing.assert_close(out["td"], td, rtol=1e-14, atol=0)
-    torch.testing.assert_close(out["w"], w, rtol=1e-14, atol=0)
-    idx = torch.arange(0, n, 2903, device=DEV)
-    ts, qs, ps = (x[idx].cpu().numpy() for x in (t, q, p))
-    with np.errstate(all="ignore"):
-        np.testing.assert_allclose(out["rh"][idx].cpu().numpy(), oracle.relative_humidity_from_specific_humidity(ts, qs, ps), rtol=1e-12)
-        np.testing.assert_allclose(td[idx].cpu().numpy(), oracle.dewpoint_from_specific_humidity(qs, ps), rtol=1e-12)
+# (the full-size properties on the benchmark's own IFS-shaped fields live in tests/test_gpu_ifs_field.py)
 
 
 # ---- host-buffer pipeline and partitioner -----------------------------------------------------------
@@ -402,6 +285,92 @@ def test_host_pipeline_equals_device_path(ek, dtype):
     dev = fused.suite_ttdp(*(torch.from_numpy(host[k]).to(DEV) for k in ("t", "td", "p")), outputs=("rh", "q"))
     for name in ("rh", "q"):
         np.testing.assert_array_equal(res[name], dev[name].cpu().numpy(), err_msg=name)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("ept_method", ["ifs", "bolton35", "bolton39"])
+def test_single_pass_suite_equals_the_ept_kernels(ek, dtype, ept_method):
+    """Slots 8 / 9 of the suites (theta_e, theta_w "direct") are the bits of the two-output ept / wet-bulb kernel and of the
+    reference-named entry points, for (t, q, p) and (t, td, p), every formulation, the run-time-mask kernel and the
+    compile-time-mask instantiations -- and equal the oracle composition under the parity rule."""
+    from ek_thermo import fused
+
+    inp = random_inputs(N_RANDOM, seed=31)
+    a = {k: np.ascontiguousarray(inp[k].astype(dtype)) for k in ("t", "q", "td", "p")}
+    d = {k: torch.from_numpy(v).to(DEV) for k, v in a.items()}
+
+    def same_bits(x, y):
+        return bool(((x == y) | (torch.isnan(x) & torch.isnan(y))).all())
+
+    for suite, hname, hum, sfx in ((fused.suite_tqp, "q", "q", "specific_humidity"), (fused.suite_ttdp, "td", "td", "dewpoint")):
+        ept, wb = fused.ept_wet_bulb(d["t"], d[hname], d["p"], humidity=hum, ept_method=ept_method, t_method="direct")
+        table = fused.SUITE_TQP_OUTPUTS if hum == "q" else fused.SUITE_TTDP_OUTPUTS
+        sets = [("ept", "wbpt"), tuple(table), ("wbpt",), ("rh", "ept")]
+        if hum == "q":
+            sets += [fused.ALL7_TQP, fused.SINGLE_PASS_TQP]
+        else:
+            sets += [fused.ALL7_TTDP, fused.SINGLE_PASS_TTDP]
+        for outputs in sets:
+            before = ek.launch_count()
+            got = suite(d["t"], d[hname], d["p"], outputs=outputs, ept_method=ept_method)
+            assert ek.launch_count() == before + 1 and tuple(got) == tuple(outputs)
+            if "ept" in got:
+                assert same_bits(got["ept"], ept), (hum, outputs)
+            if "wbpt" in got:
+                assert same_bits(got["wbpt"], wb), (hum, outputs)
+        e1 = getattr(ek.thermo, f"ept_from_{sfx}")(d["t"], d[hname], d["p"], method=ept_method)
+        w1 = getattr(ek.thermo, f"wet_bulb_potential_temperature_from_{sfx}")(d["t"], d[hname], d["p"], ept_method=ept_method)
+        assert same_bits(e1, ept) and same_bits(w1, wb)
+        for fn_name, g in ((f"ept_from_{sfx}", ept), (f"wet_bulb_potential_temperature_from_{sfx}", wb)):
+            kw = {"method": ept_method} if fn_name.startswith("ept") else {"ept_method": ept_method, "t_method": "direct"}
+            case = next(c for c in CASES if c.fn == fn_name and c.kwargs == kw)
+            args_np = [a[x] for x in case.args]
+            with np.errstate(all="ignore"):
+                want = getattr(oracle, fn_name)(*args_np, **kw)
+            compare(case, g.cpu().numpy(), want, dtype, cond=conditioning(case, args_np))
+    with pytest.raises(KeyError):
+        fused.suite_tqp(d["t"], d["q"], d["p"], outputs=("ept",), ept_method="nope")  # as the reference (T:1026)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_host_pipelines_for_every_suite(ek, dtype):
+    """The host-buffer entry points (page-locked numpy in, numpy out, chunked on three streams) for the suites with the ept /
+    wet-bulb slots and for the hybrid-level suite (2-D copies of column chunks; the pressure field crosses PCIe in neither
+    direction): bit for bit the device call, ragged chunk ends included."""
+    from ek_thermo import fused, hostpipe
+    from synthetic import IfsField
+
+    n = 1_200_011
+    inp = random_inputs(n, seed=37)
+    hs = hostpipe.HostSuite(DEV, workspace_bytes=48 << 20, n_slots=3)  # small workspace -> many chunks
+    host = {}
+    for k in ("t", "q", "td", "p"):
+        host[k] = hostpipe.pinned_empty(n, dtype)
+        host[k][:] = inp[k]
+    dev = {k: torch.from_numpy(np.array(v)).to(DEV) for k, v in host.items()}
+    for em in ("ifs", "bolton39"):
+        res = hs.suite_tqp(host["t"], host["q"], host["p"], outputs=fused.ALL7_TQP, ept_method=em)
+        want = fused.suite_tqp(dev["t"], dev["q"], dev["p"], outputs=fused.ALL7_TQP, ept_method=em)
+        for name in fused.ALL7_TQP:
+            np.testing.assert_array_equal(res[name], want[name].cpu().numpy(), err_msg=f"{name} {em}")
+    res = hs.suite_ttdp(host["t"], host["td"], host["p"], outputs=("ept", "wbpt"))
+    want = fused.suite_ttdp(dev["t"], dev["td"], dev["p"], outputs=("ept", "wbpt"))
+    for name in ("ept", "wbpt"):
+        np.testing.assert_array_equal(res[name], want[name].cpu().numpy(), err_msg=name)
+    # hybrid levels: [nlev, npl] host arrays, npl not a multiple of the chunk (ragged last chunk, non-vector tail)
+    nlev, npl = 19, 70_003
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    field = IfsField("hybrid", npl, levels=nlev, seed=5, device=DEV)
+    t_d, q_d, _ = field.materialise(0, nlev, tdt)
+    sp_d = field.sp(0).to(tdt)
+    A, B = field.A_half.astype(dtype), field.B_half.astype(dtype)
+    want = fused.suite_tq_hybrid(t_d.reshape(nlev, npl), q_d.reshape(nlev, npl), sp_d, A, B, outputs=fused.ALL7_TQP)
+    hs_small = hostpipe.HostSuite(DEV, workspace_bytes=24 << 20, n_slots=3)
+    res = hs_small.suite_tq_hybrid(t_d.reshape(nlev, npl).cpu().numpy(), q_d.reshape(nlev, npl).cpu().numpy(), sp_d.cpu().numpy(), A, B,
+                                   outputs=fused.ALL7_TQP)
+    for name in fused.ALL7_TQP:
+        assert res[name].shape == (nlev, npl)
+        np.testing.assert_array_equal(res[name], want[name].cpu().numpy(), err_msg=name)
 
 
 def test_sharded_run_equals_single_run(ek):

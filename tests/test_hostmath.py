@@ -63,3 +63,44 @@ def test_kat_reference_numbers(thermo, kat):
         got, expected = (got,), (expected,)
     for g, e in zip(got, expected):
         np.testing.assert_allclose(g.numpy(), np.asarray(e, dtype=np.float64), rtol=rtol, atol=1e-8, equal_nan=True)
+
+
+@pytest.mark.parametrize("ept_method", ["ifs", "bolton35", "bolton39"])
+@pytest.mark.parametrize("suite", ["tqp", "ttdp"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_fused_suite_functors_match_oracle(monkeypatch, suite, ept_method, dtype):
+    """The suite functors, slots 8 / 9 (ept, wbpt "direct") included: every output equals the reference function it stands
+    for (the oracle's composition) -- the run-time-mask instantiation with all ten outputs and, for "ifs", the two
+    compile-time-mask instantiations the library ships for the single pass (0x31F, 0x30D)."""
+    from ek_thermo import fused
+
+    hostmath_backend.install(monkeypatch)
+    inp = random_inputs(3000, seed=17)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    names = ("t", "q", "p") if suite == "tqp" else ("t", "td", "p")
+    a_np = [np.ascontiguousarray(inp[k].astype(dtype)) for k in names]
+    a_t = [torch.from_numpy(a.copy()).to(tdt) for a in a_np]
+    fn = fused.suite_tqp if suite == "tqp" else fused.suite_ttdp
+    table = fused.SUITE_TQP_OUTPUTS if suite == "tqp" else fused.SUITE_TTDP_OUTPUTS
+    with np.errstate(all="ignore"):
+        want = (oracle.suite_tqp if suite == "tqp" else oracle.suite_ttdp)(*a_np, ept_method=ept_method)
+    sets = [tuple(table)]
+    if ept_method == "ifs":
+        sets += [fused.ALL7_TQP if suite == "tqp" else fused.ALL7_TTDP, fused.SINGLE_PASS_TQP if suite == "tqp" else fused.SINGLE_PASS_TTDP]
+    rtol = 1e-12 if dtype == np.float64 else 1e-5
+    for outputs in sets:
+        got = fn(*a_t, outputs=outputs, ept_method=ept_method)
+        assert tuple(got) == tuple(outputs)
+        for name in outputs:
+            g, w = got[name].numpy(), np.asarray(want[name])
+            assert g.dtype == dtype
+            if dtype == np.float64:
+                assert np.array_equal(np.isnan(g), np.isnan(w)), (name, outputs)
+            else:  # float32 overflows where float64 does not (unphysical p - e -> 0 points; the oracle's "direct" fit runs in float64)
+                assert np.mean(np.isfinite(g) != np.isfinite(w)) <= 0.01, (name, outputs)
+            ok = np.isfinite(w) & np.isfinite(g)
+            rel = np.abs(g[ok].astype(np.float64) - w[ok].astype(np.float64)) / np.abs(w[ok].astype(np.float64))
+            # float32: a few points sit where the float32 formula itself is ill-conditioned (rh -> 0, p - e -> 0)
+            assert np.quantile(rel, 0.995 if dtype == np.float32 else 1.0) <= rtol, (name, outputs, rel.max())
+    with pytest.raises(KeyError):
+        fn(*a_t, outputs=("ept",), ept_method="nope")

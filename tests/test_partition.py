@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol(lib):
     missing = [n for n in names if not hasattr(so, n)]
     assert not missing, missing
     so.ek_thermo_version.restype = ctypes.c_int
-    assert so.ek_thermo_version() == 100
+    assert so.ek_thermo_version() == int(re.search(r"#define EK_THERMO_VERSION (\d+)", open(os.path.join(ROOT, "include", "ek_thermo.h")).read()).group(1))
 
 
 def test_python_binding_covers_the_reference_api():

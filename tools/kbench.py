@@ -66,7 +66,7 @@ def main():
             x[m] = float("nan")
         del m
     t, p, q, td, r = (x.to(dt) for x in (t, p, q, td, r))
-    out5 = {k: torch.empty_like(t) for k in ("theta", "es", "rh", "td", "tv", "q", "w", "e", "thetav")}
+    out5 = {k: torch.empty_like(t) for k in ("theta", "es", "rh", "td", "tv", "q", "w", "e", "thetav", "ept", "wbpt")}
 
     kernels = {
         # name: (callable, arrays touched)
@@ -82,6 +82,10 @@ def main():
         "suite_tqp_theta_rh": (lambda: fused.suite_tqp(t, q, p, outputs=("theta", "rh"), out=out5), 5),
         "suite_tqp_rh_td_w": (lambda: fused.suite_tqp(t, q, p, outputs=("rh", "td", "w"), out=out5), 6),
         "suite_ttdp5": (lambda: fused.suite_ttdp(t, td, p, out=out5), 8),
+        "single_pass_tqp": (lambda: fused.suite_tqp(t, q, p, outputs=fused.SINGLE_PASS_TQP, out=out5), 8),
+        "suite7_tqp": (lambda: fused.suite_tqp(t, q, p, outputs=fused.ALL7_TQP, out=out5), 10),
+        "suite7_ttdp": (lambda: fused.suite_ttdp(t, td, p, outputs=fused.ALL7_TTDP, out=out5), 10),
+        "suite_ept_wbpt": (lambda: fused.suite_tqp(t, q, p, outputs=("ept", "wbpt"), out=out5), 5),
         "ept_ifs_q": (lambda: thermo.ept_from_specific_humidity(t, q, p), 4),
         "ept_wbpt_direct": (lambda: fused.ept_wet_bulb(t, q, p, "q", "ifs", "direct"), 5),
         "wbpt_newton": (lambda: thermo.wet_bulb_potential_temperature_from_specific_humidity(t, q, p, t_method="newton"), 4),

@@ -13,7 +13,7 @@ from ek_thermo import fused  # noqa: E402
 
 dev = torch.device("cuda", 0)
 npl = bench.O1280_POINTS
-t, q, p = bench.make_inputs_device("tqp", 137, npl, "f64", dev, seed=0)
+t, q, p = bench.IfsField("tqp", npl, levels=137, seed=0, device=dev).materialise(0, 137, torch.float64)
 out = {k: torch.empty(npl, device=dev, dtype=torch.float64) for k in fused.DEFAULT_TQP}
 print("level  p_mean[Pa]  t_mean[K]  band_frac  ms      Gpt/s  frac")
 for k in range(0, 137, 4):
