@@ -109,7 +109,11 @@ def test_fused_suite_equals_materialised_pressure(hyb, dtype, npl):
     f32 = dtype == np.float32
     names = tuple(fused.SUITE_TQP_OUTPUTS)
     got = fused.suite_tq_hybrid(dt_, dq, dsp, a, b, outputs=names, want_p=True)
-    p_dev = vertical.pressure_on_hybrid_levels(a, b, dsp)
+    p_dev = vertical.pressure_on_hybrid_levels(a.astype(dtype), b.astype(dtype), dsp)
+    if f32:  # float64 coefficients next to a float32 sp promote the computation, as numpy does in the reference (V:630-663)
+        assert vertical.pressure_on_hybrid_levels(a, b, dsp).dtype == torch.float64
+        al = vertical.pressure_on_hybrid_levels(a.astype(dtype), b.astype(dtype), dsp, output="alpha")
+        assert al.dtype == torch.float64  # alpha / delta are xp.zeros(...) arrays in the reference: always float64 (V:672,686)
     torch.testing.assert_close(got["p"], p_dev, rtol=0, atol=0)  # same formula, same kernel family: bit-identical
     np.testing.assert_allclose(got["p"].cpu().numpy(), p_ref, rtol=2e-6 if f32 else 1e-14)
     two_step = fused.suite_tqp(dt_, dq, p_dev, outputs=names)

@@ -8,7 +8,7 @@ import torch
 
 import thermo_oracle as oracle
 from cases import CASES, edge_inputs, random_inputs
-from compare import compare, conditioning
+from compare import compare, conditioning, reference_f32_noise
 from kat import KATS
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +39,8 @@ def _run_case(ek, case, inputs, dtype):
     if not isinstance(res, tuple):
         res, want = (res,), (want,)
     conds = [None if case.iterative == "bisect" else conditioning(case, args_np, k) for k in range(len(res))]
+    if dtype == np.float32 and case.iterative != "bisect":  # float32: (conditioning, the reference's own float32 noise)
+        conds = [(c, reference_f32_noise(case, args_np, k)) for k, c in enumerate(conds)]
     return [r.cpu().numpy() for r in res], want, conds
 
 
@@ -51,7 +53,8 @@ N_RANDOM = 256 * 4 * 37 + 77
 def test_cuda_matches_oracle_random(ek, case, dtype):
     got, want, conds = _run_case(ek, case, random_inputs(N_RANDOM, seed=5), dtype)
     for g, w, c in zip(got, want, conds):
-        compare(case, g, w, dtype, cond=c)
+        c, nz = c if isinstance(c, tuple) else (c, None)
+        compare(case, g, w, dtype, cond=c, noise=nz)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
@@ -60,7 +63,8 @@ def test_cuda_matches_oracle_edge(ek, case, dtype):
     with np.errstate(all="ignore"):
         got, want, conds = _run_case(ek, case, edge_inputs(n=4099, seed=21), dtype)
     for g, w, c in zip(got, want, conds):
-        compare(case, g, w, dtype, edge=True, cond=c)
+        c, nz = c if isinstance(c, tuple) else (c, None)
+        compare(case, g, w, dtype, edge=True, cond=c, noise=nz)
 
 
 @pytest.mark.parametrize("sname,dname", [("rand", "float64"), ("edge", "float64"), ("grid", "float64"), ("ma", "float64"),
@@ -79,7 +83,9 @@ def test_cuda_matches_live_reference_fixtures(ek, ref_live, sname, dname):
         res = res if isinstance(res, tuple) else (res,)
         for k, r in enumerate(res):
             cond = None if case.iterative == "bisect" else conditioning(case, args_np, k)
-            compare(case, r.cpu().numpy(), ref_live[f"out/{sname}/{dname}/{case.id}/{k}"], dtype, edge=(sname == "edge"), cond=cond, grid=(sname in ("grid", "ma")))
+            noise = reference_f32_noise(case, args_np, k) if (dtype == np.float32 and case.iterative != "bisect") else None
+            compare(case, r.cpu().numpy(), ref_live[f"out/{sname}/{dname}/{case.id}/{k}"], dtype, edge=(sname == "edge"), cond=cond,
+                    grid=(sname in ("grid", "ma")), noise=noise)
             n += 1
     assert n > 50 or sname == "ma"
 
@@ -198,25 +204,33 @@ def test_fused_suites_match_oracle(ek, dtype):
     a = {k: np.ascontiguousarray(inp[k].astype(dtype)) for k in ("t", "q", "td", "p")}
     d = {k: torch.from_numpy(v).to(DEV) for k, v in a.items()}
     f32 = dtype == np.float32
-    rtol = 2e-5 if f32 else 1e-12
+    rtol = 1e-5 if f32 else 1e-12
 
     def check(got, suite_fn, args, names):
         with np.errstate(all="ignore"):
             want = suite_fn(*args)
             pert = [suite_fn(*[np.nextafter(a, np.asarray(np.inf, dtype=a.dtype)) if i == j else a for j, a in enumerate(args)])
                     for i in range(len(args))]
+            want64 = suite_fn(*[a.astype(np.float64) for a in args]) if f32 else None  # the reference's own float32 noise
         for name in names:
             g = got[name].cpu().numpy().astype(np.float64)
             w = np.asarray(want[name]).astype(np.float64)
-            np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg=name)
-            fin = np.isfinite(w)
+            if f32:  # the oracle's "direct" fit runs in float64 and overflows later than float32 does (SURVEY 8(c) caveat)
+                assert np.mean(np.isfinite(g) != np.isfinite(w)) < 0.002, name
+            else:
+                np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg=name)
+            fin = np.isfinite(w) & np.isfinite(g)
             den = np.maximum(np.abs(w[fin]), 1e-300)
             cond = np.zeros(den.shape)
             for pw in pert:  # 1-ulp input conditioning, see compare.conditioning
                 dlt = np.abs(np.asarray(pw[name]).astype(np.float64)[fin] - w[fin]) / den
                 cond = np.fmax(cond, np.where(np.isfinite(dlt), dlt, 0.0))
+            tol = np.maximum(rtol, 4 * cond)
+            if f32:
+                nz = np.abs(np.asarray(want64[name])[fin] - w[fin]) / den
+                tol = np.maximum(tol, 4 * np.where(np.isfinite(nz), nz, 0.0))
             rel = np.abs(g[fin] - w[fin]) / den
-            assert np.mean(rel > np.maximum(rtol, 4 * cond)) <= (0.01 if f32 else 0.0), (name, rel.max())
+            assert np.mean(rel > tol) <= (0.0005 if f32 else 0.0), (name, rel.max(), int(np.sum(rel > tol)))
 
     before = ek.launch_count()
     got = fused.suite_tqp(d["t"], d["q"], d["p"], outputs=tuple(fused.SUITE_TQP_OUTPUTS))
@@ -314,20 +328,28 @@ def test_single_pass_suite_equals_the_ept_kernels(ek, dtype, ept_method):
             before = ek.launch_count()
             got = suite(d["t"], d[hname], d["p"], outputs=outputs, ept_method=ept_method)
             assert ek.launch_count() == before + 1 and tuple(got) == tuple(outputs)
-            if "ept" in got:
-                assert same_bits(got["ept"], ept), (hum, outputs)
-            if "wbpt" in got:
-                assert same_bits(got["wbpt"], wb), (hum, outputs)
+            # a point with a NaN in ANY of its outputs is recomputed as a whole by the exact functor (libdevice math): there
+            # the other outputs agree to rounding, not bit for bit; everywhere else the bits are those of the ept kernel
+            fast = torch.ones_like(ept, dtype=torch.bool)
+            for v in got.values():
+                fast &= ~torch.isnan(v)
+            for name, ref in (("ept", ept), ("wbpt", wb)):
+                if name in got:
+                    assert bool((got[name][fast] == ref[fast]).all()), (hum, outputs, name)
+                    torch.testing.assert_close(got[name][~fast], ref[~fast], rtol=(1e-5 if dtype == np.float32 else 1e-11), atol=0, equal_nan=True)
         e1 = getattr(ek.thermo, f"ept_from_{sfx}")(d["t"], d[hname], d["p"], method=ept_method)
         w1 = getattr(ek.thermo, f"wet_bulb_potential_temperature_from_{sfx}")(d["t"], d[hname], d["p"], ept_method=ept_method)
-        assert same_bits(e1, ept) and same_bits(w1, wb)
+        both = ~torch.isnan(ept) & ~torch.isnan(wb)  # (a NaN wet bulb sends the point's ept to the exact functor as well)
+        assert same_bits(e1[both], ept[both]) and same_bits(w1[both], wb[both])
+        torch.testing.assert_close(e1, ept, rtol=(1e-5 if dtype == np.float32 else 1e-11), atol=0, equal_nan=True)
         for fn_name, g in ((f"ept_from_{sfx}", ept), (f"wet_bulb_potential_temperature_from_{sfx}", wb)):
             kw = {"method": ept_method} if fn_name.startswith("ept") else {"ept_method": ept_method, "t_method": "direct"}
             case = next(c for c in CASES if c.fn == fn_name and c.kwargs == kw)
             args_np = [a[x] for x in case.args]
             with np.errstate(all="ignore"):
                 want = getattr(oracle, fn_name)(*args_np, **kw)
-            compare(case, g.cpu().numpy(), want, dtype, cond=conditioning(case, args_np))
+            compare(case, g.cpu().numpy(), want, dtype, cond=conditioning(case, args_np),
+                    noise=(reference_f32_noise(case, args_np) if dtype == np.float32 else None))
     with pytest.raises(KeyError):
         fused.suite_tqp(d["t"], d["q"], d["p"], outputs=("ept",), ept_method="nope")  # as the reference (T:1026)
 
@@ -613,7 +635,7 @@ def test_host_array_front_end_numpy_semantics(ek):
         t32 = t.astype(np.float32)
         g32 = host.thermo.saturation_vapour_pressure(t32)
         assert g32.dtype == np.float32
-        np.testing.assert_allclose(g32, oracle.saturation_vapour_pressure(t32), rtol=2e-5)
+        np.testing.assert_allclose(g32, oracle.saturation_vapour_pressure(t32), rtol=1e-5)
         assert host.thermo.potential_temperature(t32, p).dtype == np.float64
         # lists and integers, Python scalars only (numpy scalar out), zero-size input
         np.testing.assert_allclose(host.thermo.celsius_to_kelvin([0, 10, 20]), [273.16, 283.16, 293.16], rtol=1e-15)

@@ -13,7 +13,7 @@ import torch
 import hostmath_backend
 import thermo_oracle as oracle
 from cases import CASES, edge_inputs, random_inputs
-from compare import compare, conditioning
+from compare import compare, conditioning, reference_f32_noise
 from kat import KATS
 
 
@@ -33,6 +33,8 @@ def _run_case(thermo, case, inputs, dtype):
     if not isinstance(res, tuple):
         res, want = (res,), (want,)
     conds = [None if case.iterative == "bisect" else conditioning(case, args_np, k) for k in range(len(res))]
+    if dtype == np.float32 and case.iterative != "bisect":  # float32: (conditioning, the reference's own float32 noise)
+        conds = [(c, reference_f32_noise(case, args_np, k)) for k, c in enumerate(conds)]
     return [r.numpy() for r in res], want, conds
 
 
@@ -42,7 +44,8 @@ def test_functors_match_oracle_random(thermo, case, dtype):
     inputs = random_inputs(3000, seed=5)
     got, want, conds = _run_case(thermo, case, inputs, dtype)
     for g, w, c in zip(got, want, conds):
-        compare(case, g, w, dtype, cond=c)
+        c, nz = c if isinstance(c, tuple) else (c, None)
+        compare(case, g, w, dtype, cond=c, noise=nz)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.id for c in CASES])
@@ -52,7 +55,8 @@ def test_functors_match_oracle_edge(thermo, case, dtype):
         inputs = edge_inputs(n=600, seed=21)
         got, want, conds = _run_case(thermo, case, inputs, dtype)
     for g, w, c in zip(got, want, conds):
-        compare(case, g, w, dtype, edge=True, cond=c)
+        c, nz = c if isinstance(c, tuple) else (c, None)
+        compare(case, g, w, dtype, edge=True, cond=c, noise=nz)
 
 
 @pytest.mark.parametrize("kat", KATS, ids=[f"{i}-{k[0]}" for i, k in enumerate(KATS)])
