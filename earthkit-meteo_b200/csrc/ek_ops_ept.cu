@@ -30,7 +30,7 @@ static int bisect_prepare(void* stream) {
 static int bisect_prepare(void*) { return EK_OK; }
 #endif
 
-template <typename T, int M, int TM>
+template <typename T, int M, int TM, int HUM = -1>
 static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p0, void* ept_out, void* wb_out, int64_t n, void* stream) {
     ek_operand ins[3] = {t, h, p};
     void* outs[2] = {ept_out, TM == TM_NONE ? nullptr : wb_out};
@@ -41,14 +41,17 @@ static int ept_wb_mt(ek_operand t, ek_operand h, ek_operand p, int hum, int at_p
         const int rc = bisect_prepare(stream);
         if (rc != EK_OK) return rc;
     }
-    return launch<EK_OPS(OpEptWb<M, TM>), T>("ept_wet_bulb", ins, outs, n, P, stream);
+    return launch<EK_OPS(OpEptWb<M, TM, HUM>), T>("ept_wet_bulb", ins, outs, n, P, stream);
 }
 
 template <typename T, int M>
 static int ept_wb_m(int tm, ek_operand t, ek_operand h, ek_operand p, int hum, int at_p0, void* e, void* w, int64_t n, void* s) {
     switch (tm) {
-        case EK_TM_NONE: return ept_wb_mt<T, M, TM_NONE>(t, h, p, hum, at_p0, e, w, n, s);
-        case EK_TM_DIRECT: return ept_wb_mt<T, M, TM_DIRECT>(t, h, p, hum, at_p0, e, w, n, s);
+        // the two HBM-bound forms get one instantiation per humidity kind (see OpEptWb)
+        case EK_TM_NONE:
+            return hum ? ept_wb_mt<T, M, TM_NONE, 1>(t, h, p, hum, at_p0, e, w, n, s) : ept_wb_mt<T, M, TM_NONE, 0>(t, h, p, hum, at_p0, e, w, n, s);
+        case EK_TM_DIRECT:
+            return hum ? ept_wb_mt<T, M, TM_DIRECT, 1>(t, h, p, hum, at_p0, e, w, n, s) : ept_wb_mt<T, M, TM_DIRECT, 0>(t, h, p, hum, at_p0, e, w, n, s);
         case EK_TM_BISECT: return ept_wb_mt<T, M, TM_BISECT>(t, h, p, hum, at_p0, e, w, n, s);
         case EK_TM_NEWTON: return ept_wb_mt<T, M, TM_NEWTON>(t, h, p, hum, at_p0, e, w, n, s);
     }

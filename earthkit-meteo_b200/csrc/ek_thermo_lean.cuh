@@ -43,6 +43,11 @@
 #ifndef EK_LEAN_LOG_HILO
 #define EK_LEAN_LOG_HILO 1  // 1: k*ln2 added as a hi/lo pair (abs error of log_ ~2e-16); 0: one FMA less, ~1.5 ulp of the result
 #endif
+#ifndef EK_LEAN_IMM
+#define EK_LEAN_IMM 1  // 1: the constants whose low 32 bits are zero (+-0.5, -0.25, the 1.5*2^52 rounding constant) are written as
+                       // literals: they become 32-bit immediates of DFMA / DADD instead of occupying uniform registers, and a
+                       // polynomial step fma(r, c1, c0) no longer needs two constant operands (only one fits an instruction)
+#endif
 
 namespace ek {
 namespace lean {
@@ -131,6 +136,8 @@ __device__ __forceinline__ double log_(double x) {
     const double s = fma(r, p, kLog[0]);
 #elif EK_LOG_DEG == 5
     const double s = fma(r2, fma(r, kLog[3], kLog[2]), fma(r, kLog[1], kLog[0]));
+#elif EK_LEAN_IMM
+    const double s = fma(r2, -0.25, fma(r, kLog[1], -0.5));
 #else
     const double s = fma(r2, kLog[2], fma(r, kLog[1], kLog[0]));
 #endif
@@ -146,9 +153,15 @@ __device__ __forceinline__ double log_(double x) {
 
 __device__ __forceinline__ double exp_(double x) {
     const bool bad = (unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x40862000u;  // |x| >= 708, inf, NaN: answer NaN
+#if EK_LEAN_IMM
+    const double t = fma(x, kRed[0], 0x1.8p52);
+    const int ki = __double2loint(t);
+    const double kd = t - 0x1.8p52;
+#else
     const double t = fma(x, kRed[0], kRed[5]);
     const int ki = __double2loint(t);
     const double kd = t - kRed[5];
+#endif
     double r = fma(kd, -kRed[1], x);
     r = fma(kd, -kRed[2], r);
     const double T = lds_exp(ki & (EK_EXP_TAB_N - 1));
@@ -158,6 +171,8 @@ __device__ __forceinline__ double exp_(double x) {
     const double s = fma(r2, fma(r, kExp[3], kExp[2]), fma(r, kExp[1], kExp[0]));
 #elif EK_EXP_DEG == 4
     const double s = fma(r2, kExp[2], fma(r, kExp[1], kExp[0]));
+#elif EK_LEAN_IMM
+    const double s = fma(r, kExp[1], 0.5);
 #else
     const double s = fma(r, kExp[1], kExp[0]);
 #endif

@@ -34,6 +34,9 @@
 #ifndef EK_LEAN_MATH
 #define EK_LEAN_MATH 0
 #endif
+#ifndef EK_LEAN_DJ_MERGED
+#define EK_LEAN_DJ_MERGED 1  // lean build: Davies-Jones lcl fit with its constants merged (see lcl_t_davies)
+#endif
 
 #if EK_LEAN_MATH && defined(__CUDA_ARCH__)
 #define EK_LEAN_DEVICE 1
@@ -50,7 +53,7 @@ struct Consts {
     double Rd, Rv_m_Rd, kappa, lambda, p0, inv_p0, eps, c_vp, c1_tv, eps_m1, T0, TI;
     double C1, inv_C1, C3W, C4W, C3I, C4I, slope_w, slope_i, band, inv_band, d_alpha_c, C3W_T0;
     double K0_ifs, neg_K0_ifs, neg_lam_K0_ifs;
-    double dj_a, dj_b, dj_c;                      // Davies-Jones lcl fit (T:961)
+    double dj_a, dj_b, dj_c, dj_a0;               // Davies-Jones lcl fit (T:961); dj_a0 = dj_a - (dj_b - dj_c) T0
     double b35_K3, neg_lam_b35_K0;               // T:1202-1203
     double b39_K1, b39_K2, b39_K4, b39_2K2, neg_b39_K1, neg_lam_b39_K0, neg_lam_b39_K1;  // T:1263-1266
     double wa0, wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4, inv_t0;  // wbpt "direct" rational fit (T:1051-1052)
@@ -103,6 +106,7 @@ constexpr Consts make_consts() {
     k.dj_a = 0.212;
     k.dj_b = 1.571e-3;
     k.dj_c = 4.36e-4;
+    k.dj_a0 = 0.212 - (1.571e-3 - 4.36e-4) * cdef::T0;
     k.b35_K3 = 0.28;
     k.neg_lam_b35_K0 = -cdef::lambda * 2675.0;
     k.b39_K1 = 1.78;

@@ -88,7 +88,7 @@ def compare(case, got, want, dtype, edge=False, cond=None, grid=False, noise=Non
         # float32 near overflow/underflow: a 1-ulp difference decides inf vs finite vs NaN, and the reference's
         # float32 "direct" path evaluates its polynomials in float64 (SURVEY.md 8(c) caveat)
         nonfin_g, nonfin_w = ~np.isfinite(got), ~np.isfinite(want)
-        assert np.mean(nonfin_g != nonfin_w) < (0.02 if edge else 0.002), f"non-finite positions differ: {case.id}"
+        assert np.mean(nonfin_g != nonfin_w) < (0.02 if edge else 0.005), f"non-finite positions differ: {case.id}"
         fin = ~(nonfin_g | nonfin_w)
     else:
         if bisect:

@@ -28,6 +28,7 @@ def ek():
 @pytest.fixture(scope="module")
 def o1280(ek):
     """BASELINE.json configs[1] / [2]: the O1280 x 137 float64 field of `bench.py` (seed 0 = rank 0's field)."""
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 100e9:
         pytest.skip("needs ~95 GB of free HBM")
@@ -139,9 +140,10 @@ def test_config4_ens_shard_on_the_bench_field(ek):
     n_total, slab = 51 * 137 * O640_POINTS, O640_POINTS
     b, e = partition.shard_range(n_total, 8, 3, align=slab)
     assert (e - b) in (873 * slab, 874 * slab)
+    torch.cuda.empty_cache()  # blocks the caching allocator still holds from earlier tests do not count as free
     free, _ = torch.cuda.mem_get_info()
-    if free < 90e9:
-        pytest.skip("needs ~85 GB of free HBM")
+    if free < 110e9:
+        pytest.skip("needs ~105 GB of free HBM")
     field = IfsField("tqp", slab, levels=137, seed=0, device=DEV)
     arrays = field.materialise(b // slab, (e - b) // slab, torch.float64)
     t, q, p = arrays

@@ -21,14 +21,19 @@ import torch  # noqa: E402
 from ek_thermo import host, hostpipe  # noqa: E402
 
 
+LAST = []
+
+
 def best(fn, reps=3):
     fn()
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        fn()
+        r = fn()
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
+        del r
+    LAST[:] = ts
     return min(ts)
 
 
@@ -50,9 +55,25 @@ def main():
         for kind, arrs in (("pageable", (t, p, q)), ("pinned in, pageable out", (tp, pp, qp))):
             dt = best(lambda: fn(*arrs))
             rows.append((f"host.thermo.{name}", kind, n / dt / 1e9, bpp * n / dt / 1e9))
-    for kind, arrs in (("pageable", (t, q, p)), ("pinned in, pageable out", (tp, qp, pp))):
-        dt = best(lambda: host.fused.suite_tqp(*arrs))
-        rows.append(("host.fused.suite_tqp (5 outputs)", kind, n / dt / 1e9, 64 * n / dt / 1e9))
+    from ek_thermo import fused
+
+    for outputs in (("ept", "wbpt"), fused.DEFAULT_TQP, fused.ALL7_TQP):
+        for pinned_results in (True, False):
+            prev = host.set_pinned_results(pinned_results)
+            for kind, arrs in (("pageable in", (t, q, p)), ("pinned in", (tp, qp, pp))):
+                dt = best(lambda: host.fused.suite_tqp(*arrs, outputs=outputs), reps=4)
+                rows.append((f"host.fused.suite_tqp ({len(outputs)} outputs)", f"{kind}, {'page-locked' if pinned_results else 'pageable'} results",
+                             n / dt / 1e9, 8 * (3 + len(outputs)) * n / dt / 1e9))
+                print(f"  reps [s] {outputs} pinned_results={pinned_results} {kind}: " + " ".join(f"{x:.3f}" for x in LAST), flush=True)
+            host.set_pinned_results(prev)
+    t0 = time.perf_counter()
+    blocks = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    t1 = time.perf_counter()
+    del blocks
+    blocks = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    t2 = time.perf_counter()
+    del blocks
+    print(f"  page-locked allocation of 4 x {8 * n / 1e6:.0f} MB: first {t1 - t0:.3f} s, again (torch's caching host allocator) {t2 - t1:.3f} s")
     hs = hostpipe.HostSuite("cuda:0", workspace_bytes=1536 << 20, n_slots=3)
     outs = {k: hostpipe.pinned_empty(n) for k in ("theta", "es", "rh", "td", "tv")}
     dt = best(lambda: hs.suite_tqp(tp, qp, pp, outputs=tuple(outs), out=outs))
