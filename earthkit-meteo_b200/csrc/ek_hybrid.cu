@@ -25,22 +25,38 @@ using namespace ek;
 // levels whose t/q loads are in flight per thread.  Measured on B200 (O1280 x 137, fp64): 2 -> 10.3-11.0 ms,
 // 3 -> 12.0 ms, 4 -> 13.9 ms (register pressure at the 64-register cap), so 2.
 #ifndef EK_HYB_LU
-#define EK_HYB_LU 2
+#define EK_HYB_LU 3
 #endif
 #ifndef EK_HYB_PREFETCH
-#define EK_HYB_PREFETCH 0  // L2 prefetch of the next level pair: measured within the run-to-run noise (10.6-11.5 ms either way), off
+#define EK_HYB_PREFETCH 1  // L2 prefetch of a later level pair (EK_HYB_PF_DIST pairs ahead).  ncu on the round-1 kernel: 7.4 warps
+                           // per issue slot waiting on global loads, DRAM at 79 % -- the level loop keeps too few bytes in flight
+#endif
+#ifndef EK_HYB_PF_DIST
+#define EK_HYB_PF_DIST 2  // measured: 2 pairs ahead 0.86 vs 0.83 (hybrid suite), geometric height 0.91 vs 0.88
+#endif
+#ifndef EK_COL_PREFETCH
+#define EK_COL_PREFETCH 1  // the same for the column (geopotential) kernel
+#endif
+#ifndef EK_COL_PF_DIST
+#define EK_COL_PF_DIST 2
 #endif
 #ifndef EK_COL_LU
 #define EK_COL_LU 2  // levels in flight in the column (geopotential) kernel; measured 2 -> 4.46 ms, 4 -> 5.40 ms, 6 -> 7.68 ms
                      // (O1280 x 137 fp64: beyond 2 the 64-register cap spills)
 #endif
 
-// resident CTAs per SM the register budget of the two level-loop kernels is sized for
+// Resident CTAs per SM the register budget of the two level-loop kernels is sized for.  Measured on B200 (O1280 x 137 fp64,
+// profiles/r02_ab_hybrid.log, with the L2 prefetch on): 3 CTAs (80 registers, no spills of the column state) beat 4 (64) for
+// the hybrid suite (0.70 -> 0.86 of the roofline) and the thickness / geopotential forms (0.885 -> 0.926); the geometric-height
+// forms keep 4 (0.877 vs 0.825 with 3).
 #ifndef EK_HYBS_MIN_CTAS
-#define EK_HYBS_MIN_CTAS EK_MIN_CTAS
+#define EK_HYBS_MIN_CTAS 2  // with three levels in flight (EK_HYB_LU): 0.87 stable, against 0.80-0.88 for 3 CTAs x 2 levels
 #endif
 #ifndef EK_COL_MIN_CTAS
-#define EK_COL_MIN_CTAS EK_MIN_CTAS
+#define EK_COL_MIN_CTAS 3
+#endif
+#ifndef EK_COL_MIN_CTAS_GEOM
+#define EK_COL_MIN_CTAS_GEOM 4
 #endif
 
 namespace {
@@ -99,6 +115,22 @@ template <typename T, bool VECOK> __device__ __forceinline__ void st_row(T* row,
     }
 }
 
+// delta / alpha rows of a float32 launch stored as float64 (what the reference returns: it allocates them with xp.zeros(...),
+// V:672,686): the float32 values, widened in the store
+template <bool VECOK> __device__ __forceinline__ void st_row_f64(double* row, int64_t i0, int64_t npl, const float* v) {
+    if (VECOK) {
+        __stcs(reinterpret_cast<double2*>(row + i0), make_double2((double)v[0], (double)v[1]));
+        __stcs(reinterpret_cast<double2*>(row + i0 + 2), make_double2((double)v[2], (double)v[3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < npl) __stcs(row + i0 + j, (double)v[j]);
+    }
+}
+template <bool VECOK> __device__ __forceinline__ void st_row_f64(double* row, int64_t i0, int64_t npl, const double* v) {
+    st_row<double, VECOK>(row, i0, npl, v);
+}
+
 struct HybridArgs {
     const void* sp;
     const void* A;         // nhalf half-level coefficients (device)
@@ -112,6 +144,7 @@ struct HybridArgs {
     void *full, *half, *delta, *alpha;
     int64_t npl;
     int rows_per_item;
+    int ad_f64;  // delta / alpha are float64 arrays whatever T is
 };
 
 template <typename T, bool VECOK>
@@ -149,8 +182,13 @@ __global__ void __launch_bounds__(kThreads, EK_MIN_CTAS) hybrid_pressure_kernel(
                 }
                 const int64_t off = (int64_t)r * g.npl;
                 if (g.full) st_row<T, VECOK>(static_cast<T*>(g.full) + off, i0, g.npl, f);
-                if (g.delta) st_row<T, VECOK>(static_cast<T*>(g.delta) + off, i0, g.npl, d);
-                if (g.alpha) st_row<T, VECOK>(static_cast<T*>(g.alpha) + off, i0, g.npl, al);
+                if (g.ad_f64) {
+                    if (g.delta) st_row_f64<VECOK>(static_cast<double*>(g.delta) + off, i0, g.npl, d);
+                    if (g.alpha) st_row_f64<VECOK>(static_cast<double*>(g.alpha) + off, i0, g.npl, al);
+                } else {
+                    if (g.delta) st_row<T, VECOK>(static_cast<T*>(g.delta) + off, i0, g.npl, d);
+                    if (g.alpha) st_row<T, VECOK>(static_cast<T*>(g.alpha) + off, i0, g.npl, al);
+                }
             }
             if (r < g.n_half && g.half != nullptr) {
                 const int h = g.half_rows[r];
@@ -181,6 +219,23 @@ struct SuiteHybridArgs {
     int rows_per_item;
 };
 
+// Half-level coefficients in shared memory, behind the lean tables: A[0..nhalf), then B[0..nhalf), as T.  One copy per CTA;
+// reads in the level loop are warp-uniform (broadcast).  (Through the read-only global path the compiler hoisted the four
+// loads of a level far above their use and spilled them: 8 local-memory round trips per level at the 64-register cap.)
+template <typename T> __device__ __forceinline__ T* coef_smem() {
+    extern __shared__ __align__(16) unsigned char ek_smem_raw[];
+    return reinterpret_cast<T*>(ek_smem_raw + (sizeof(T) == 8 ? kSmemBytes : 0u));
+}
+template <typename T> __device__ __forceinline__ void coef_smem_fill(const T* A, const T* B, int first, int n) {
+    T* c = coef_smem<T>();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        c[i] = __ldg(A + first + i);
+        c[n + i] = __ldg(B + first + i);
+    }
+    __syncthreads();
+}
+template <typename T> constexpr unsigned coef_smem_bytes(int nhalf) { return 2u * (unsigned)nhalf * (unsigned)sizeof(T); }
+
 template <class Op, class OpE, typename T, bool VECOK>
 __global__ void __launch_bounds__(kThreads, EK_HYBS_MIN_CTAS) suite_hybrid_kernel(const SuiteHybridArgs g, const Params P) {
     constexpr int VEC = Vec16<T>::N;
@@ -189,8 +244,10 @@ __global__ void __launch_bounds__(kThreads, EK_HYBS_MIN_CTAS) suite_hybrid_kerne
 #if EK_LEAN_DEVICE
     if (sizeof(T) == 8) lean::init_tables();
 #endif
-    const T* A = static_cast<const T*>(g.A);
-    const T* B = static_cast<const T*>(g.B);
+    const int nhalf = g.nlev + 1;
+    coef_smem_fill<T>(static_cast<const T*>(g.A), static_cast<const T*>(g.B), 0, nhalf);
+    const T* sA = coef_smem<T>();
+    const T* sB = sA + nhalf;
     const T* tq[2] = {static_cast<const T*>(g.t), static_cast<const T*>(g.q)};
     const int64_t ptiles = (g.npl + TILE - 1) / TILE;
     const int chunks = (g.nlev + g.rows_per_item - 1) / g.rows_per_item;
@@ -201,8 +258,13 @@ __global__ void __launch_bounds__(kThreads, EK_HYBS_MIN_CTAS) suite_hybrid_kerne
         const int k1 = min(k0 + g.rows_per_item, g.nlev);
         const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
         if (i0 >= g.npl) continue;
-        T sp[VEC];
+        T sp[VEC], ph[VEC];  // ph: pressure of the half level on top of the current level, carried down the column
         ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+        {
+            const T a0 = sA[k0], b0 = sB[k0];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) ph[j] = exactm::hyb_half(a0, b0, sp[j]);  // V:663
+        }
         for (int k = k0; k < k1; k += LU) {
             T x[LU][2][VEC];
 #pragma unroll
@@ -213,21 +275,23 @@ __global__ void __launch_bounds__(kThreads, EK_HYBS_MIN_CTAS) suite_hybrid_kerne
                 }
 #if EK_HYB_PREFETCH
 #pragma unroll
-            for (int u = 0; u < LU; ++u)  // ask L2 for the next pair of levels while this pair is being computed
-                if (k + LU + u < k1) {
+            for (int u = 0; u < LU; ++u)  // ask L2 for a later pair of levels while this pair is being computed
+                if (k + LU * EK_HYB_PF_DIST + u < k1) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(tq[c] + (int64_t)(k + LU + u) * g.npl + i0));
+                    for (int c = 0; c < 2; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(tq[c] + (int64_t)(k + LU * EK_HYB_PF_DIST + u) * g.npl + i0));
                 }
 #endif
 #pragma unroll
             for (int u = 0; u < LU; ++u) {
                 if (k + u >= k1) break;
                 const int kk = k + u;
-                const T a0 = __ldg(A + kk), b0 = __ldg(B + kk), a1 = __ldg(A + kk + 1), b1 = __ldg(B + kk + 1);
+                const T a1 = sA[kk + 1], b1 = sB[kk + 1];
                 T y[S_NSLOTS][VEC], pf[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    pf[j] = exactm::hyb_full(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]));
+                    const T ph1 = exactm::hyb_half(a1, b1, sp[j]);
+                    pf[j] = exactm::hyb_full(ph[j], ph1);  // V:708; the same two half-level values the reference forms
+                    ph[j] = ph1;
                     T a[3] = {x[u][0][j], x[u][1][j], pf[j]}, r[S_NSLOTS];
                     point<Op, OpE, T>(a, r, P, 3u);  // t and q are the array inputs; p is derived
 #pragma unroll
@@ -261,11 +325,13 @@ struct GeoArgs {
 
 // One thread walks VEC columns from the bottom level to the top one: d = R(q) t, dphi_k = sum_{j>k} d_j delta_j + d_k alpha_k
 // (V:799-810, same accumulation order as the reference's flipped cumulative sum).  alpha/delta come from registers
-// (sp, A, B) or from memory (GIVEN_AD).  Loads of two levels are in flight before the math of the lower one.
+// (sp and the half-level coefficients in shared memory; the pressure of the half level under the current level is carried
+// up the column, so a level forms one new half-level pressure) or from memory (GIVEN_AD).  Loads of two levels are in
+// flight before the math of the lower one.
 // MODE >= 0: the output form is a compile-time constant (the registers of zs / geom(zs) and the form choices drop out of
 // the level loop where they are not needed); MODE = -1: taken from g.mode at run time (the rarer launch shapes).
 template <typename T, bool GIVEN_AD, bool VECOK, int MODE>
-__global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential_kernel(const GeoArgs g) {
+__global__ void __launch_bounds__(kThreads, (MODE >= EK_HM_GEOM_SEA ? EK_COL_MIN_CTAS_GEOM : EK_COL_MIN_CTAS)) column_geopotential_kernel(const GeoArgs g) {
     const int mode = MODE >= 0 ? MODE : g.mode;
     constexpr int VEC = Vec16<T>::N;
     constexpr int TILE = kThreads * VEC;
@@ -276,17 +342,27 @@ __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential
 #if EK_LEAN_DEVICE
     if (sizeof(T) == 8) lean::init_tables();
 #endif
-    const T* A = static_cast<const T*>(g.A);
-    const T* B = static_cast<const T*>(g.B);
+    const T* sA = nullptr;
+    const T* sB = nullptr;
+    if (!GIVEN_AD) {  // the band's nlev + 1 half-level coefficients
+        coef_smem_fill<T>(static_cast<const T*>(g.A), static_cast<const T*>(g.B), g.band0, g.nlev + 1);
+        sA = coef_smem<T>();
+        sB = sA + (g.nlev + 1);
+    }
     const T* arr[4] = {static_cast<const T*>(g.t), static_cast<const T*>(g.q), static_cast<const T*>(g.alpha), static_cast<const T*>(g.delta)};
     const int64_t ptiles = (g.npl + TILE - 1) / TILE;
     for (int64_t pt = blockIdx.x; pt < ptiles; pt += gridDim.x) {
         const int64_t i0 = pt * TILE + (int64_t)threadIdx.x * VEC;
         if (i0 >= g.npl) continue;
-        T sp[VEC], zs[VEC], hsub[VEC], sum[VEC];
+        T sp[VEC], zs[VEC], hsub[VEC], sum[VEC], phb[VEC];  // phb: pressure of the half level under the current level
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) sp[j] = zs[j] = hsub[j] = sum[j] = T(0);
-        if (!GIVEN_AD) ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+        for (int j = 0; j < VEC; ++j) sp[j] = zs[j] = hsub[j] = sum[j] = phb[j] = T(0);
+        if (!GIVEN_AD) {
+            ld_row<T, VECOK>(static_cast<const T*>(g.sp), i0, g.npl, sp, false);
+            const T ab = sA[g.nlev], bb = sB[g.nlev];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) phb[j] = exactm::hyb_half(ab, bb, sp[j]);  // V:663
+        }
         const bool add_zs = mode != EK_HM_THICKNESS && mode != EK_HM_GH_GROUND;
         if (add_zs) ld_row<T, VECOK>(static_cast<const T*>(g.zs), i0, g.npl, zs, false);
         // The six output forms (V:1064-1069, V:1163-1188) as one expression: z = dphi (+ zs), then nothing / z/g / the
@@ -305,14 +381,20 @@ __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential
 #pragma unroll
                     for (int c = 0; c < NARR; ++c) ld_row<T, VECOK>(arr[c] + (int64_t)(k - u) * g.npl, i0, g.npl, x[u][c], true);
                 }
+#if EK_COL_PREFETCH
+#pragma unroll
+            for (int u = 0; u < CLU; ++u)
+                if (k - CLU * EK_COL_PF_DIST - u >= 0) {
+#pragma unroll
+                    for (int c = 0; c < NARR; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(arr[c] + (int64_t)(k - CLU * EK_COL_PF_DIST - u) * g.npl + i0));
+                }
+#endif
 #pragma unroll
             for (int u = 0; u < CLU; ++u) {
                 const int kk = k - u;
                 if (kk < 0) break;
-                T a0 = T(0), b0 = T(0), a1 = T(0), b1 = T(0);
-                if (!GIVEN_AD) {
-                    a0 = __ldg(A + g.band0 + kk), b0 = __ldg(B + g.band0 + kk), a1 = __ldg(A + g.band0 + kk + 1), b1 = __ldg(B + g.band0 + kk + 1);
-                }
+                T a0 = T(0), b0 = T(0);
+                if (!GIVEN_AD) a0 = sA[kk], b0 = sB[kk];
                 const bool top = g.top_toa && kk == 0;
                 T y[VEC];
 #pragma unroll
@@ -322,7 +404,9 @@ __global__ void __launch_bounds__(kThreads, EK_COL_MIN_CTAS) column_geopotential
                         al = x[u][2][j];
                         de = x[u][3][j];
                     } else {
-                        delta_alpha<T>(exactm::hyb_half(a0, b0, sp[j]), exactm::hyb_half(a1, b1, sp[j]), top, static_cast<T>(g.alpha_top), de, al);
+                        const T pht = exactm::hyb_half(a0, b0, sp[j]);  // the half level on top of this level (V:663)
+                        delta_alpha<T>(pht, phb[j], top, static_cast<T>(g.alpha_top), de, al);
+                        phb[j] = pht;
                     }
                     const T d = exactm::gas_constant(x[u][1][j]) * x[u][0][j];
                     // the running sum starts at 0: 0 + x is x, so the bottom level needs no special case
@@ -367,7 +451,7 @@ bool ok16(const void* p) { return p == nullptr || aligned16(p); }
 template <typename T>
 static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows, int n_full,
                                           const int* half_rows, int n_half, int top_k, int top_toa, double alpha_top, void* full, void* half,
-                                          void* delta, void* alpha, void* stream) {
+                                          void* delta, void* alpha, int alpha_delta_f64, void* stream) {
     const char* what = "pressure_on_hybrid_levels";
     if (!A || !B || !sp || nhalf < 2 || npl < 0 || n_full < 0 || n_half < 0) return set_error(EK_ERR_ARG, "%s: bad arguments", what);
     if (!full && !half && !delta && !alpha) return set_error(EK_ERR_ARG, "%s: no output buffer given", what);
@@ -375,7 +459,7 @@ static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhal
     if (half && (n_half < 1 || !half_rows)) return set_error(EK_ERR_ARG, "%s: half needs half_rows", what);
     if (npl == 0) return EK_OK;
     HybridArgs g{sp, A, B, full_rows, half_rows, (full || delta || alpha) ? n_full : 0, half ? n_half : 0, top_k, top_toa, alpha_top,
-                 full, half, delta, alpha, npl, 2};
+                 full, half, delta, alpha, npl, 2, (alpha_delta_f64 || sizeof(T) == 8) ? 1 : 0};
     constexpr int TILE = kThreads * Vec16<T>::N;
     const int64_t ptiles = (npl + TILE - 1) / TILE;
     const int n_rows = g.n_full > g.n_half ? g.n_full : g.n_half;
@@ -396,8 +480,8 @@ static int impl_pressure_on_hybrid_levels(const void* A, const void* B, int nhal
 }
 EK_API(pressure_on_hybrid_levels,
        (const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows, int n_full, const int* half_rows, int n_half,
-        int top_k, int top_toa, double alpha_top, void* full, void* half, void* delta, void* alpha, void* stream),
-       (A, B, nhalf, sp, npl, full_rows, n_full, half_rows, n_half, top_k, top_toa, alpha_top, full, half, delta, alpha, stream))
+        int top_k, int top_toa, double alpha_top, void* full, void* half, void* delta, void* alpha, int alpha_delta_f64, void* stream),
+       (A, B, nhalf, sp, npl, full_rows, n_full, half_rows, n_half, top_k, top_toa, alpha_top, full, half, delta, alpha, alpha_delta_f64, stream))
 
 template <typename T>
 static int impl_hybrid_top_is_toa(const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream) {
@@ -430,19 +514,21 @@ static int impl_geopotential_on_hybrid_levels(const void* t, const void* q, int 
     if (blocks < 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
     const bool vec = npl % Vec16<T>::N == 0 && ok16(t) && ok16(q) && ok16(sp) && ok16(alpha) && ok16(delta) && ok16(zs) && ok16(out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned smem = smem_for<T>() + (given ? 0u : coef_smem_bytes<T>(nlev + 1));  // lean tables + the band's half-level coefficients
+    if (smem > 200u * 1024u) return set_error(EK_ERR_ARG, "%s: nlev=%d is too large for the shared-memory coefficient copy", what, nlev);
     if (given) {
-        if (vec) launch_kernel<&column_geopotential_kernel<T, true, true, -1>, T>(blocks, st, g);
-        else launch_kernel<&column_geopotential_kernel<T, true, false, -1>, T>(blocks, st, g);
+        if (vec) launch_kernel_smem<&column_geopotential_kernel<T, true, true, -1>>(blocks, st, smem, g);
+        else launch_kernel_smem<&column_geopotential_kernel<T, true, false, -1>>(blocks, st, smem, g);
     } else if (!vec) {
-        launch_kernel<&column_geopotential_kernel<T, false, false, -1>, T>(blocks, st, g);
+        launch_kernel_smem<&column_geopotential_kernel<T, false, false, -1>>(blocks, st, smem, g);
     } else {  // the whole-field case: one instantiation per output form
         switch (mode) {
-            case EK_HM_THICKNESS: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_THICKNESS>, T>(blocks, st, g); break;
-            case EK_HM_GEOPOTENTIAL: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOPOTENTIAL>, T>(blocks, st, g); break;
-            case EK_HM_GH_SEA: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GH_SEA>, T>(blocks, st, g); break;
-            case EK_HM_GH_GROUND: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GH_GROUND>, T>(blocks, st, g); break;
-            case EK_HM_GEOM_SEA: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_SEA>, T>(blocks, st, g); break;
-            default: launch_kernel<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_GROUND>, T>(blocks, st, g); break;
+            case EK_HM_THICKNESS: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_THICKNESS>>(blocks, st, smem, g); break;
+            case EK_HM_GEOPOTENTIAL: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_GEOPOTENTIAL>>(blocks, st, smem, g); break;
+            case EK_HM_GH_SEA: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_GH_SEA>>(blocks, st, smem, g); break;
+            case EK_HM_GH_GROUND: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_GH_GROUND>>(blocks, st, smem, g); break;
+            case EK_HM_GEOM_SEA: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_SEA>>(blocks, st, smem, g); break;
+            default: launch_kernel_smem<&column_geopotential_kernel<T, false, true, EK_HM_GEOM_GROUND>>(blocks, st, smem, g); break;
         }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -481,12 +567,14 @@ static int suite_hybrid(const void* t, const void* q, const void* sp, const void
     Params P;
     P.out_mask = out_mask;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define EK_LAUNCH_SH(M, EM)                                                                              \
-    do {                                                                                                 \
-        if (vec)                                                                                         \
-            launch_kernel<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, true>, T>(blocks, st, g, P);  \
-        else                                                                                             \
-            launch_kernel<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, false>, T>(blocks, st, g, P); \
+    const unsigned smem = smem_for<T>() + coef_smem_bytes<T>(nlev + 1);  // lean tables (float64) + the half-level coefficients
+    if (smem > 200u * 1024u) return set_error(EK_ERR_ARG, "%s: nlev=%d is too large for the shared-memory coefficient copy", what, nlev);
+#define EK_LAUNCH_SH(M, EM)                                                                                         \
+    do {                                                                                                            \
+        if (vec)                                                                                                    \
+            launch_kernel_smem<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, true>>(blocks, st, smem, g, P);     \
+        else                                                                                                        \
+            launch_kernel_smem<&suite_hybrid_kernel<OpM<M, EM>, OpME<M, EM>, T, false>>(blocks, st, smem, g, P);    \
     } while (0)
     if (ept_method == EK_EPT_BOLTON35)
         EK_LAUNCH_SH(0, EPT_BOLTON35);

@@ -29,6 +29,9 @@
 #ifndef EK_MAX_THREADS
 #define EK_MAX_THREADS 256
 #endif
+#ifndef EK_PF_DIST
+#define EK_PF_DIST 1  // tiles ahead of the current one that prefetch_tile_l2 asks L2 for (functors with PREFETCH_NEXT)
+#endif
 #ifndef EK_MIN_CTAS
 #define EK_MIN_CTAS 4  // <= 64 registers per thread: 4 CTAs = 32 warps per SM hide the fp64 dependency chains
 #endif
@@ -323,7 +326,7 @@ __device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutAr
     for (; ta < ntiles; ta += G) {
         TileRegs<Op, T, UNROLL> A;
         load_tile<Op, T, UNROLL, VECOK, ALLARR>(A, in, ta * TILE + toff);
-        if (Op::PREFETCH_NEXT && ta + G < ntiles) prefetch_tile_l2<Op, T, UNROLL>(in, (ta + G) * TILE + toff);
+        if (Op::PREFETCH_NEXT && ta + EK_PF_DIST * G < ntiles) prefetch_tile_l2<Op, T, UNROLL>(in, (ta + EK_PF_DIST * G) * TILE + toff);
         compute_store_tile<Op, OpE, T, UNROLL, VECOK>(A, out, ta * TILE + toff, P, array_mask);
     }
 #endif

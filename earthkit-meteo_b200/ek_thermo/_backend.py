@@ -106,7 +106,7 @@ _c_int_p = ctypes.POINTER(c_int)
 for _sfx in ("f64", "f32"):
     _fn = getattr(_lib, f"ek_thermo_pressure_on_hybrid_levels_{_sfx}")
     _fn.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double,
-                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     _fn.restype = c_int
     _fn = getattr(_lib, f"ek_thermo_hybrid_top_is_toa_{_sfx}")
     _fn.argtypes = [c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p]

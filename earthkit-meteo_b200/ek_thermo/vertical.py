@@ -112,16 +112,15 @@ def pressure_on_hybrid_levels(A, B, sp, levels=None, alpha_top="ifs", output="fu
     for name in _OUTPUTS:
         if name in want:
             nrow = len(half_rows) if name == "half" else len(full_rows)
-            res[name] = torch.empty((nrow,) + tuple(sp.shape), dtype=dtype, device=dev)
+            # alpha / delta: xp.zeros(...) arrays in the reference, i.e. always float64 (V:672,686); the kernel widens on store
+            odt = torch.float64 if name in ("alpha", "delta") else dtype
+            res[name] = torch.empty((nrow,) + tuple(sp.shape), dtype=odt, device=dev)
     ptr = lambda n: c_void_p(res[n].data_ptr()) if n in res else c_void_p(None)  # noqa: E731
     if npl > 0:
         _b.call_raw("pressure_on_hybrid_levels", dtype, dev, c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), c_int(nhalf),
                     c_void_p(spc.data_ptr()), c_int64(npl), c_void_p(rows_f.data_ptr()), c_int(len(full_rows)), c_void_p(rows_h.data_ptr()),
                     c_int(len(half_rows)), c_int(top_k), c_int(top_toa), c_double(math.log(2.0) if alpha_top == "ifs" else 1.0),
-                    ptr("full"), ptr("half"), ptr("delta"), ptr("alpha"))
-    for name in ("alpha", "delta"):  # the reference allocates these with xp.zeros(...), i.e. always float64 (V:672,686):
-        if name in res and dtype != torch.float64:  # float32 values, stored in a float64 array
-            res[name] = res[name].to(torch.float64)
+                    ptr("full"), ptr("half"), ptr("delta"), ptr("alpha"), c_int(1))
     outs = [res[o] for o in output]
     if vertical_axis != 0 and outs[0].dim() > 1:  # V:731-733
         outs = [r.movedim(0, vertical_axis) for r in outs]

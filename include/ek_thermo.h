@@ -163,10 +163,11 @@ EK_THERMO_FN(coriolis, ek_operand lat, void* out, int64_t n, void* stream)      
  * full-level index k = level number - 1), `half` one row per entry of half_rows (half-level index).  top_k is the
  * full level treated as the column top (the first level of the computed band, V:645-647), top_toa the field-wide
  * decision any(p_half[top] <= 0.1 Pa) (V:678; ek_thermo_hybrid_top_is_toa computes it), alpha_top = ln 2 ("ifs")
- * or 1.0 ("arpege") (V:669). */
+ * or 1.0 ("arpege") (V:669).  alpha_delta_f64 = 1: `delta` and `alpha` are float64 arrays also in the _f32 entry point -- the
+ * reference allocates them with xp.zeros(...), i.e. float64, whatever the dtype of sp (V:672,686). */
 EK_THERMO_FN(pressure_on_hybrid_levels, const void* A, const void* B, int nhalf, const void* sp, int64_t npl, const int* full_rows,
              int n_full, const int* half_rows, int n_half, int top_k, int top_toa, double alpha_top, void* full, void* half, void* delta,
-             void* alpha, void* stream)
+             void* alpha, int alpha_delta_f64, void* stream)
 /* ORs 1 into *flag (a zero-initialised DEVICE int) when any(a_top + b_top * sp <= 0.1) (V:678) */
 EK_THERMO_FN(hybrid_top_is_toa, const void* sp, int64_t npl, double a_top, double b_top, int* flag, void* stream)
 /* geopotential thickness / geopotential / height of hybrid full levels (V:741-1188): d = R(q) t per

@@ -124,3 +124,25 @@ def test_host_array_front_end_has_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             host.thermo.potential_temperature(np.full(4, 280.0), np.full(4, 9.0e4))
+
+
+def test_bench_shard_plan_partitions_the_ensemble():
+    """bench.py's partitioned workload (BASELINE.json configs[3]): the ranks' slab ranges tile the 51 x 137 slabs of the
+    ensemble without gap or overlap for every world size the driver uses; a shard that does not fit in HBM is capped and
+    says so; the weak workloads give every rank the whole per-GPU field."""
+    import bench
+    from ek_thermo import partition
+
+    wl = bench.WORKLOADS["conv_ens_o640_f64"]
+    total = 51 * 137
+    for world in (1, 2, 4, 8):
+        plans = [bench.shard_plan(wl, world, r) for r in range(world)]
+        edges = []
+        for r in range(world):
+            b, e = partition.shard_range(total * wl["npl"], world, r, align=wl["npl"])
+            edges.append((b // wl["npl"], e // wl["npl"]))
+            assert plans[r][0] == edges[-1][0]
+            assert plans[r][1] == min(edges[-1][1] - edges[-1][0], 1880) and plans[r][2] == (edges[-1][1] - edges[-1][0] > 1880)
+        assert edges[0][0] == 0 and edges[-1][1] == total and all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+        assert all(p[2] for p in plans) == (world < 4)  # 4 and 8 GPUs hold the whole ensemble, 1 and 2 are capped at 150 GB
+    assert bench.shard_plan(bench.WORKLOADS["suite_tqp_o1280x137_f64"], 8, 5) == (0, 137, False)
