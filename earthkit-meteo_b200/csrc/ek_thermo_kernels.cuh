@@ -30,7 +30,14 @@
 #define EK_MAX_THREADS 256
 #endif
 #ifndef EK_PF_DIST
-#define EK_PF_DIST 1  // tiles ahead of the current one that prefetch_tile_l2 asks L2 for (functors with PREFETCH_NEXT)
+#define EK_PF_DIST 2  // tiles ahead of the current one that prefetch_tile_l2 asks L2 for (functors with PREFETCH_NEXT)
+#endif
+#ifndef EK_HEAVY_MIN_CTAS
+#define EK_HEAVY_MIN_CTAS 3  // resident CTAs per SM for the functors that declare HEAVY (the fused suites, ept / ept + wet bulb):
+                             // 80 registers instead of 64 -- no spills in their ~200-instruction bodies -- and, with the L2 prefetch
+                             // two tiles ahead covering what the fourth CTA's loads covered, 3-6 % more of the roofline
+                             // (profiles/r02_ab_ew.log: suite 0.886 -> 0.923, ept + wet bulb 0.80 -> 0.86, single pass 0.76 -> 0.84);
+                             // the short single-output kernels lose 7-10 % with it (theta 0.974 -> 0.871) and keep EK_MIN_CTAS
 #endif
 #ifndef EK_MIN_CTAS
 #define EK_MIN_CTAS 4  // <= 64 registers per thread: 4 CTAs = 32 warps per SM hide the fp64 dependency chains
@@ -195,6 +202,14 @@ template <class Op> struct UnrollOf<Op, decltype((void)Op::UNROLL)> {
     static constexpr int value = Op::UNROLL > 0 ? Op::UNROLL : EK_UNROLL;
 };
 
+// Resident CTAs per SM a functor's register budget is sized for: EK_MIN_CTAS, or EK_HEAVY_MIN_CTAS where the functor says HEAVY.
+template <class Op, class = void> struct MinCtasOf {
+    static constexpr int value = EK_MIN_CTAS;
+};
+template <class Op> struct MinCtasOf<Op, decltype((void)Op::HEAVY)> {
+    static constexpr int value = Op::HEAVY ? EK_HEAVY_MIN_CTAS : EK_MIN_CTAS;
+};
+
 // The inputs of one tile, per thread: UNROLL 16-byte vectors of every input array, in registers.
 template <class Op, typename T, int UNROLL> struct TileRegs {
     T x[Op::NIN][UNROLL][Vec16<T>::N];
@@ -333,7 +348,7 @@ __device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutAr
 }
 
 template <class Op, class OpE, typename T, int UNROLL>
-__global__ void __launch_bounds__(kThreads, EK_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
     ew_kernel(const InArgs<Op::NIN> in, const OutArgs<Op::NOUT> out, const int64_t n, const Params P, const int vec_ok) {
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;

@@ -246,6 +246,11 @@ def _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device):
     nres = 0
     nchunks = -(-n // _STAGE_CHUNK)
 
+    n_pageable = sum(1 for x in pinned if not x)
+    # every array's chunk is copied in pieces by several workers at once: one memcpy stream per array (3 for a suite) leaves
+    # most of the host's memory bandwidth unused and makes the staging step the bottleneck of the whole pipeline
+    parts = max(1, min(4, pool._max_workers // max(1, n_pageable)))
+
     def fill(ci):
         """Worker threads copy chunk ci of every pageable input into the slot's staging buffers."""
         slot = ci % S
@@ -253,12 +258,23 @@ def _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device):
         e = min(n, b + _STAGE_CHUNK)
         if h2d_done[slot] is not None:
             h2d_done[slot].synchronize()
-        return [pool.submit(np.copyto, st_set.buf(dt, slot, "in", k).numpy()[: e - b], a[b:e]) for k, (_, a) in enumerate(flat) if not pinned[k]]
+        futs = []
+        step = -(-(e - b) // parts)
+        for k, (_, a) in enumerate(flat):
+            if pinned[k]:
+                continue
+            dst = st_set.buf(dt, slot, "in", k).numpy()
+            for o in range(0, e - b, step):
+                m = min(step, e - b - o)
+                futs.append(pool.submit(np.copyto, dst[o:o + m], a[b + o:b + o + m]))
+        return futs
 
     def copy_out(slot):
         b, e = ranges[slot]
         events[slot].synchronize()
-        pending[slot] = [pool.submit(np.copyto, outs[j][b:e], st_set.buf(dt, slot, "out", j).numpy()[: e - b]) for j in range(nres)]
+        step = -(-(e - b) // max(1, min(4, pool._max_workers // max(1, nres))))
+        pending[slot] = [pool.submit(np.copyto, outs[j][b + o:min(e, b + o + step)], st_set.buf(dt, slot, "out", j).numpy()[o:min(e - b, o + step)])
+                         for j in range(nres) for o in range(0, e - b, step)]
 
     futs = fill(0)
     for ci in range(nchunks):

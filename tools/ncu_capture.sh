@@ -1,14 +1,15 @@
 #!/bin/bash
 # One `ncu --set full` capture per kernel of interest (one launch each, after the warm-up launches), exported on the GPU
 # box as raw-page CSVs (the .ncu-rep files are too large to bring back; pass KEEP_REP=1 to keep them).
-#   tools/ncu_capture.sh <tag> <workload> <kernel regex> [extra bench args]
-# e.g. tools/ncu_capture.sh suite_tqp_f64 suite_tqp_o1280x137_f64 'ew_kernel.*OpSuiteTQPm'
+#   tools/ncu_capture.sh <tag> <kernel base-name regex> <launches to skip> <command ...>
+# e.g. tools/ncu_capture.sh suite_tqp_f64 ew_kernel 3 python bench.py --workload suite_tqp_o1280x137_f64 --steps 2 --warmup 3 --no-cpu --no-e2e --no-parity
+# (ncu matches the regex against the function's base name: every streaming kernel is "ew_kernel", so pick the launch by
+# running a command that launches only the kernel of interest and skipping its warm-up launches)
 set -u
-tag=$1; wl=$2; re=$3; shift 3
+tag=$1; re=$2; skip=$3; shift 3
 mkdir -p gpurun_out
 rep=gpurun_out/r02_ncu_full_${tag}
-ncu --set full --clock-control none --import-source on -k "regex:${re}" --launch-skip 3 -c 1 -f -o ${rep} \
-    python bench.py --workload ${wl} --steps 2 --warmup 3 --no-cpu --no-e2e --no-parity "$@" > ${rep}.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:${re}" --launch-skip ${skip} -c 1 -f -o ${rep} "$@" > ${rep}.log 2>&1
 ncu -i ${rep}.ncu-rep --page raw --csv > ${rep}_raw.csv 2>> ${rep}.log
 python - <<PY
 import csv
