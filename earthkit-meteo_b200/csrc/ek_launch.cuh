@@ -87,7 +87,12 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     const int64_t tail_blocks = ((n - ntiles * tile) + threads - 1) / threads;
     const int sms = sm_count_current_device();
     if (sms <= 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
-    const int64_t cap = (int64_t)sms * g_ctas_per_sm.load(std::memory_order_relaxed);
+    int64_t cap = (int64_t)sms * g_ctas_per_sm.load(std::memory_order_relaxed);
+    // small fields (a few tiles per resident CTA, e.g. one ERA5 level): exactly one resident wave -- every CTA copies the lean
+    // tables once and walks its 2-3 tiles back to back instead of a second, partial wave of CTAs queueing behind the first
+    // (theta + rh on 1 M points, graph replay: 14.4 -> 12.3 us; profiles/r02_kbench_era5_ctas.log)
+    const int64_t wave = (int64_t)sms * MinCtasOf<Op>::value;
+    if (ntiles <= 8 * wave && wave < cap) cap = wave;
     int64_t blocks = ntiles > tail_blocks ? ntiles : tail_blocks;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -97,6 +102,68 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    return EK_OK;
+}
+
+// Op over n_seg separate fields of n_per_seg points each in one launch (ew_batch_kernel).  ins[k]: host array of n_seg device
+// pointers, or NULL for the broadcast scalar scalars[k]; outs[o]: host array of n_seg device pointers, or NULL when output o
+// is not wanted.  More than kBatchMaxSeg segments take one launch per kBatchMaxSeg.
+template <class Op, class OpE, typename T>
+int launch_batch(const char* what, int n_seg, const void* const* const* ins, const double* scalars, void* const* const* outs, int64_t n_per_seg,
+                 Params P, void* stream) {
+    if (n_seg < 0 || n_per_seg < 0) return set_error(EK_ERR_ARG, "%s: n_seg=%d n_per_seg=%lld", what, n_seg, (long long)n_per_seg);
+    uint32_t in_mask = 0, out_mask = 0;
+    for (int k = 0; k < Op::NIN; ++k)
+        if (ins[k]) in_mask |= 1u << k;
+    for (int o = 0; o < Op::NOUT; ++o)
+        if (outs[o]) out_mask |= 1u << o;
+    if (out_mask == 0) return set_error(EK_ERR_ARG, "%s: no output buffer given", what);
+    P.out_mask = out_mask;
+    if (n_seg == 0 || n_per_seg == 0) return EK_OK;
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return set_error(EK_ERR_ARG, "%s: no CUDA device is current", what);
+    constexpr int unroll = UnrollOf<Op>::value;
+    const int64_t tile = (int64_t)kThreads * Vec16<T>::N * unroll;
+    for (int s0 = 0; s0 < n_seg; s0 += kBatchMaxSeg) {
+        BatchArgs<Op::NIN, Op::NOUT> B;
+        B.n_seg = n_seg - s0 < kBatchMaxSeg ? n_seg - s0 : kBatchMaxSeg;
+        B.in_mask = in_mask;
+        B.out_mask = out_mask;
+        int vec_ok = n_per_seg % Vec16<T>::N == 0 ? 1 : 0;
+        for (int k = 0; k < Op::NIN; ++k) {
+            B.s[k] = scalars ? scalars[k] : 0.0;
+            for (int j = 0; j < B.n_seg; ++j) {
+                B.in[k][j] = ins[k] ? ins[k][s0 + j] : nullptr;
+                if (ins[k]) {
+                    if (!B.in[k][j] || reinterpret_cast<uintptr_t>(B.in[k][j]) % sizeof(T))
+                        return set_error(EK_ERR_ARG, "%s: input %d of segment %d is NULL or not aligned to its element size", what, k, s0 + j);
+                    if (!aligned16(B.in[k][j])) vec_ok = 0;
+                }
+            }
+        }
+        for (int o = 0; o < Op::NOUT; ++o)
+            for (int j = 0; j < B.n_seg; ++j) {
+                B.out[o][j] = outs[o] ? outs[o][s0 + j] : nullptr;
+                if (outs[o]) {
+                    if (!B.out[o][j] || reinterpret_cast<uintptr_t>(B.out[o][j]) % sizeof(T))
+                        return set_error(EK_ERR_ARG, "%s: output %d of segment %d is NULL or not aligned to its element size", what, o, s0 + j);
+                    if (!aligned16(B.out[o][j])) vec_ok = 0;
+                }
+            }
+        const int64_t ntiles = (n_per_seg / tile) * B.n_seg;
+        const int64_t tail_blocks = ((n_per_seg % tile) * B.n_seg + kThreads - 1) / kThreads;
+        int64_t cap = (int64_t)sms * g_ctas_per_sm.load(std::memory_order_relaxed);
+        const int64_t wave = (int64_t)sms * MinCtasOf<Op>::value;
+        if (ntiles <= 8 * wave && wave < cap) cap = wave;
+        int64_t blocks = ntiles > tail_blocks ? ntiles : tail_blocks;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        prepare_smem<&ew_batch_kernel<Op, OpE, T, unroll>>(smem_for<T>());
+        ew_batch_kernel<Op, OpE, T, unroll><<<(unsigned)blocks, kThreads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(B, n_per_seg, P, vec_ok);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    }
     return EK_OK;
 }
 

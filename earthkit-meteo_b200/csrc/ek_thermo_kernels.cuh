@@ -202,6 +202,13 @@ template <class Op> struct UnrollOf<Op, decltype((void)Op::UNROLL)> {
     static constexpr int value = Op::UNROLL > 0 ? Op::UNROLL : EK_UNROLL;
 };
 
+template <class Op, class = void> struct DeferColdOf {
+    static constexpr bool value = false;
+};
+template <class Op> struct DeferColdOf<Op, decltype((void)Op::DEFER_COLD)> {
+    static constexpr bool value = Op::DEFER_COLD;
+};
+
 // Resident CTAs per SM a functor's register budget is sized for: EK_MIN_CTAS, or EK_HEAVY_MIN_CTAS where the functor says HEAVY.
 template <class Op, class = void> struct MinCtasOf {
     static constexpr int value = EK_MIN_CTAS;
@@ -284,6 +291,36 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
             for (int v = 0; v < VEC; ++v)
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o) y[o][v] = res[v][o];
+        } else if constexpr (DeferColdOf<Op>::value && EK_LEAN_DEVICE) {
+            // Functors that declare DEFER_COLD: the VEC points of a vector go through the fast functor back to back and are
+            // checked for NaN afterwards -- one basic block, so the scheduler interleaves their dependency chains (these fp64
+            // kernels wait on fixed-latency results: ept 0.83 -> 0.93, ept + wet bulb 0.87 -> 0.89, es 0.63 -> 0.66 of the
+            // roofline, profiles/r02_ab_ew3.log).  The multi-output suites lose 2-5 % with it (registers) and keep point().
+            T res[VEC][NOUT];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                T a[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) res[v][o] = T(0);
+                Op::template apply<T>(a, res[v], P);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if ((sizeof(T) == 8 || ColdF32<Op>::value) && __builtin_expect(any_nan<NOUT>(res[v]), 0)) {
+                    T a2[NIN], r2[NOUT];
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k) a2[k] = r.x[k][u][v];
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) r2[o] = res[v][o];
+                    cold_point<OpE, T>(a2, r2, P, array_mask);
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) res[v][o] = r2[o];
+                }
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) y[o][v] = res[v][o];
+            }
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -379,6 +416,70 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
             const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
             if (w) __stcs(static_cast<T*>(out.p[o]) + i, r[o]);
         }
+    }
+}
+
+// ---- batched launch: the same functor over n_seg separate fields of n_per_seg points each, ONE launch ------------------
+// For callers that hold a model field level by level (one allocation per level, e.g. the fields of a GRIB message list):
+// a launch per 1 M-point level is bound by launch + table-copy + pipeline-fill latency (12-16 us for 6 us of HBM time), a
+// single launch over all levels is not.  The per-segment pointers travel in the kernel parameters (constant bank, indexed
+// with the warp-uniform segment number).  Every point goes through point(): results are the bits of the per-field launch.
+constexpr int kBatchMaxSeg = 128;
+template <int NIN, int NOUT> struct BatchArgs {
+    const void* in[NIN][kBatchMaxSeg];
+    void* out[NOUT][kBatchMaxSeg];
+    double s[NIN];       // broadcast scalar of input k when in[k][0] == NULL (the same for every segment)
+    uint32_t in_mask;    // bit k: input k is an array
+    uint32_t out_mask;   // bit o: output o is written
+    int n_seg;
+};
+
+template <class Op, class OpE, typename T, int UNROLL>
+__global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
+    ew_batch_kernel(const __grid_constant__ BatchArgs<Op::NIN, Op::NOUT> B, const int64_t n_per_seg, const Params P, const int vec_ok) {
+    constexpr int NIN = Op::NIN;
+    constexpr int NOUT = Op::NOUT;
+    constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
+#if EK_LEAN_DEVICE
+    if (sizeof(T) == 8) lean::init_tables();
+#endif
+    const int64_t tiles_per_seg = n_per_seg / TILE;
+    const int64_t ntiles = tiles_per_seg * B.n_seg;
+    const int64_t toff = (int64_t)threadIdx.x * Vec16<T>::N;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int seg = (int)(tile / tiles_per_seg);
+        const int64_t base = (tile - (int64_t)seg * tiles_per_seg) * TILE + toff;
+        InArgs<NIN> in;
+        OutArgs<NOUT> out;
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) {
+            in.p[k] = ((B.in_mask >> k) & 1u) ? B.in[k][seg] : nullptr;
+            in.s[k] = B.s[k];
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) out.p[o] = ((B.out_mask >> o) & 1u) ? B.out[o][seg] : nullptr;
+        TileRegs<Op, T, UNROLL> A;
+        if (vec_ok) {
+            load_tile<Op, T, UNROLL, true, false>(A, in, base);
+            compute_store_tile<Op, OpE, T, UNROLL, true>(A, out, base, P, B.in_mask);
+        } else {
+            load_tile<Op, T, UNROLL, false, false>(A, in, base);
+            compute_store_tile<Op, OpE, T, UNROLL, false>(A, out, base, P, B.in_mask);
+        }
+    }
+    // tails: fewer than one tile of points per segment, one point per thread
+    const int64_t tail = n_per_seg - tiles_per_seg * TILE;
+    const int64_t tail_total = tail * B.n_seg;
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < tail_total; j += (int64_t)gridDim.x * kThreads) {
+        const int seg = (int)(j / tail);
+        const int64_t i = tiles_per_seg * TILE + (j - (int64_t)seg * tail);
+        T a[NIN], r[NOUT];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) a[k] = ((B.in_mask >> k) & 1u) ? __ldcs(static_cast<const T*>(B.in[k][seg]) + i) : static_cast<T>(B.s[k]);
+        point<Op, OpE, T>(a, r, P, B.in_mask);
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o)
+            if ((B.out_mask >> o) & 1u) __stcs(static_cast<T*>(B.out[o][seg]) + i, r[o]);
     }
 }
 

@@ -102,6 +102,11 @@ for _name in ("suite_tqp", "suite_ttdp"):
         _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
         _fn.argtypes = [ek_operand] * 3 + [ctypes.POINTER(c_void_p), c_uint32, c_int, c_int64, c_void_p]
         _fn.restype = c_int
+for _name in ("suite_tqp_batch", "suite_ttdp_batch"):
+    for _sfx in ("f64", "f32"):
+        _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
+        _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_double), ctypes.POINTER(c_void_p), c_uint32, c_int, c_int64, c_void_p]
+        _fn.restype = c_int
 _c_int_p = ctypes.POINTER(c_int)
 for _sfx in ("f64", "f32"):
     _fn = getattr(_lib, f"ek_thermo_pressure_on_hybrid_levels_{_sfx}")
@@ -354,6 +359,64 @@ def execute_suite(symbol: str, args, out_names, slots, out=None, ept_method=0):
         mask |= 1 << k
     if n > 0:
         _call(symbol, dtype, dev, [*ops, ptrs, mask, ept_method, n])
+    del keep
+    return res
+
+
+def execute_suite_batch(symbol: str, seg_args, out_names, slots, outs=None, ept_method=0):
+    """Run a fused suite over a list of separate fields in one launch.  seg_args: three items, each a list of same-shape
+    contiguous CUDA tensors (one per field) or a Python number (broadcast).  Returns a list of {name: tensor}, one per field."""
+    lists = [a for a in seg_args if isinstance(a, (list, tuple))]
+    if not lists:
+        raise TypeError("ek_thermo: a batched suite needs at least one list of CUDA tensors")
+    n_seg = len(lists[0])
+    if any(len(a) != n_seg for a in lists):
+        raise ValueError("ek_thermo: the input lists of a batched suite must have one length")
+    res = [dict() for _ in range(n_seg)]
+    if n_seg == 0:
+        return res
+    first = lists[0][0]
+    dtype, dev, shape = first.dtype, first.device, first.shape
+    if dtype not in _SUFFIX:
+        raise TypeError("ek_thermo: batched suites take float64 or float32 tensors")
+    keep = []
+    ptr_arrays = []
+    scalars = (c_double * 3)(0.0, 0.0, 0.0)
+    for k, a in enumerate(seg_args):
+        if isinstance(a, (list, tuple)):
+            for t in a:
+                if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                    raise TypeError("ek_thermo: got a non-CUDA tensor. This package only runs on CUDA tensors (no CPU fallback)")
+                if t.dtype != dtype or t.device != dev or t.shape != shape or not t.is_contiguous():
+                    raise ValueError("ek_thermo: the fields of a batched suite must share dtype, device and shape and be contiguous")
+            arr = (c_void_p * n_seg)(*[t.data_ptr() for t in a])
+            keep.append(arr)
+            ptr_arrays.append(ctypes.cast(arr, c_void_p))
+        elif isinstance(a, (int, float)) and not isinstance(a, bool):
+            scalars[k] = float(a)
+            ptr_arrays.append(c_void_p(None))
+        else:
+            raise TypeError("ek_thermo: batched suite arguments are lists of CUDA tensors or Python numbers")
+    out_tab = (c_void_p * N_SUITE_SLOTS)()
+    mask = 0
+    for name, k in zip(out_names, slots):
+        col = []
+        for j in range(n_seg):
+            t = outs[j].get(name) if outs is not None else None
+            if t is not None:
+                if t.dtype != dtype or t.shape != shape or not t.is_contiguous() or t.device != dev:
+                    raise ValueError(f"ek_thermo: preallocated output {name!r} of field {j} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+            else:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+            res[j][name] = t
+            col.append(t.data_ptr())
+        arr = (c_void_p * n_seg)(*col)
+        keep.append(arr)
+        out_tab[k] = ctypes.cast(arr, c_void_p)
+        mask |= 1 << k
+    n = first.numel()
+    if n > 0:
+        _call(symbol, dtype, dev, [n_seg, *ptr_arrays, scalars, out_tab, mask, ept_method, n])
     del keep
     return res
 

@@ -72,6 +72,23 @@ def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None, ept_method="ifs"):
     return _b.execute_suite("suite_ttdp", (t, td, p), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out, _ept_id(ept_method))
 
 
+def suite_tqp_batch(ts, qs, ps, outputs=DEFAULT_TQP, out=None, ept_method="ifs"):
+    """``suite_tqp`` over a LIST of separate fields (one tensor per level / member, each its own allocation) in one launch.
+
+    ``ts`` / ``qs`` / ``ps`` are lists of same-shape contiguous CUDA tensors, or a Python number for a broadcast operand (a
+    pressure level).  Returns ``[{name: tensor}, ...]``, one dict per field; every value is bit-identical to
+    ``suite_tqp(ts[j], qs[j], ps[j])``.  A launch per 1 M-point level is bound by launch and pipeline-fill latency
+    (12-16 us for 6 us of HBM time); one launch over all levels is not."""
+    outputs = tuple(outputs)
+    return _b.execute_suite_batch("suite_tqp_batch", (ts, qs, ps), outputs, _slots(SUITE_TQP_OUTPUTS, outputs), out, _ept_id(ept_method))
+
+
+def suite_ttdp_batch(ts, tds, ps, outputs=DEFAULT_TTDP, out=None, ept_method="ifs"):
+    """``suite_ttdp`` over a list of separate fields in one launch (see ``suite_tqp_batch``)."""
+    outputs = tuple(outputs)
+    return _b.execute_suite_batch("suite_ttdp_batch", (ts, tds, ps), outputs, _slots(SUITE_TTDP_OUTPUTS, outputs), out, _ept_id(ept_method))
+
+
 def suite_tq_hybrid(t, q, sp, A, B, outputs=DEFAULT_TQP, out=None, want_p=False, ept_method="ifs"):
     """The (t, q, p) suite on hybrid model levels with the pressure computed inside the kernel.
 

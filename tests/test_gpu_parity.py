@@ -395,6 +395,49 @@ def test_host_pipelines_for_every_suite(ek, dtype):
         np.testing.assert_array_equal(res[name], want[name].cpu().numpy(), err_msg=name)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_batched_suite_equals_per_field_launches(ek, dtype):
+    """One launch over a list of separately allocated levels (the per-level caller's layout) = one suite launch per level, bit
+    for bit: compile-time and run-time output sets, every ept formulation, a broadcast pressure level, more fields than one
+    launch's pointer table holds, a ragged field length (tile body + tail) and 16-byte-unaligned fields (scalar path)."""
+    from ek_thermo import fused
+
+    n_seg, n = 150, 256 * 4 * 3 + 77  # > 128 segments: two launches
+    inp = random_inputs(n_seg * n + 1, seed=41)
+    flat = {k: torch.from_numpy(inp[k]).to(DEV).to(dtype) for k in ("t", "q", "td", "p")}
+
+    def fields(name, off=0):
+        return [flat[name][off + j * n: off + (j + 1) * n].clone() if off == 0 else flat[name][off + j * n: off + (j + 1) * n] for j in range(n_seg)]
+
+    def same(a, b):
+        return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+
+    ts, qs, tds, ps = (fields(k) for k in ("t", "q", "td", "p"))
+    for outputs, em in ((fused.DEFAULT_TQP, "ifs"), (("theta", "rh"), "ifs"), (fused.ALL7_TQP, "ifs"), (tuple(fused.SUITE_TQP_OUTPUTS), "bolton39"), (("w", "ept"), "bolton35")):
+        before = ek.launch_count()
+        got = fused.suite_tqp_batch(ts, qs, ps, outputs=outputs, ept_method=em)
+        assert ek.launch_count() == before + 2 and len(got) == n_seg
+        for j in (0, 1, 127, 128, n_seg - 1):
+            want = fused.suite_tqp(ts[j], qs[j], ps[j], outputs=outputs, ept_method=em)
+            for name in outputs:
+                assert same(got[j][name], want[name]), (outputs, em, j, name)
+    got = fused.suite_ttdp_batch(ts, tds, 85000.0, outputs=fused.ALL7_TTDP)  # a pressure level: scalar operand
+    for j in (0, 77, n_seg - 1):
+        want = fused.suite_ttdp(ts[j], tds[j], 85000.0, outputs=fused.ALL7_TTDP)
+        for name in fused.ALL7_TTDP:
+            assert same(got[j][name], want[name]), (j, name)
+    # views at an odd element offset: not 16-byte aligned -> the scalar load/store path of the same kernel
+    tv, qv, pv = (fields(k, off=1) for k in ("t", "q", "p"))
+    got = fused.suite_tqp_batch(tv, qv, pv)
+    for j in (0, 5, n_seg - 1):
+        want = fused.suite_tqp(tv[j], qv[j], pv[j])
+        for name in fused.DEFAULT_TQP:
+            assert same(got[j][name], want[name]), (j, name)
+    assert fused.suite_tqp_batch([], [], []) == []
+    with pytest.raises(ValueError):
+        fused.suite_tqp_batch(ts, qs[:-1], ps)
+
+
 def test_sharded_run_equals_single_run(ek):
     """The partitioner's shards, run one by one on this GPU, reproduce the unsharded result exactly."""
     from ek_thermo import fused, partition
