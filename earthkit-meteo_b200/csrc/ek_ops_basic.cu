@@ -138,3 +138,14 @@ static int impl_lcl(ek_operand t, ek_operand td, ek_operand p, int method, void*
 }
 EK_API(lcl, (ek_operand t, ek_operand td, ek_operand p, int method, void* t_lcl, void* p_lcl, int64_t n, void* stream),
        (t, td, p, method, t_lcl, p_lcl, n, stream))
+
+// ---- height forms of a geopotential ---------------------------------------------------
+template <typename T> static int impl_height_from_thickness(ek_operand dphi, ek_operand zs, int mode, void* out, int64_t n, void* stream) {
+    if (mode < 0 || mode > 6) return set_error(EK_ERR_ENUM, "height_from_thickness: invalid mode %d", mode);
+    ek_operand ins[2] = {dphi, zs};
+    void* outs[1] = {out};
+    Params P;
+    P.opt0 = mode;
+    return launch<EK_OPS(OpHeightForm), T>("height_from_thickness", ins, outs, n, P, stream);
+}
+EK_API(height_from_thickness, (ek_operand dphi, ek_operand zs, int mode, void* out, int64_t n, void* stream), (dphi, zs, mode, out, n, stream))

@@ -90,6 +90,8 @@ SIGNATURES = {
     "wind_polar_to_xy": (2, (c_int,), 2),
     "w_from_omega": (3, (), 1),
     "coriolis": (1, (), 1),
+    # height forms of a geopotential
+    "height_from_thickness": (2, (c_int,), 1),
 }
 
 for _name, (_nin, _opts, _nout) in SIGNATURES.items():

@@ -165,8 +165,11 @@ def _column_kernel(t, q, mode, vertical_axis, sp=None, A=None, B=None, alpha_top
     p_sp = p_a = p_b = p_al = p_de = p_zs = null
     nhalf = top_toa = 0
     if alpha is not None:
-        if alpha.shape != t.shape or delta.shape != t.shape:
-            raise ValueError("alpha and delta must have the shape of t")
+        if alpha.shape != t.shape or delta.shape != t.shape:  # numpy broadcasting of d * alpha, d * delta into zeros_like(d) (V:804-810)
+            try:
+                alpha, delta = alpha.expand(t.shape), delta.expand(t.shape)
+            except RuntimeError:
+                raise ValueError(f"operands could not be broadcast together with shapes {tuple(t.shape)} {tuple(alpha.shape)}") from None
         ac, dc = alpha.to(dtype).contiguous(), delta.to(dtype).contiguous()
         keep += [ac, dc]
         p_al, p_de = c_void_p(ac.data_ptr()), c_void_p(dc.data_ptr())
@@ -196,15 +199,55 @@ def relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, q, alph
     return _column_kernel(t, q, 0, vertical_axis, alpha=alpha, delta=delta)
 
 
+def _thickness_axis_as_reference(t, q, A, B, sp, alpha_top, vertical_axis):
+    """``vertical_axis != 0`` exactly as the reference computes it (V:970-994): alpha / delta come out of
+    ``pressure_on_hybrid_levels`` with their level axis FIRST and are then moved with ``moveaxis(x, vertical_axis, 0)`` like
+    t and q -- a second move.  That is shape-consistent only for square fields (as many columns as levels), where it
+    scrambles alpha / delta; any other shape fails numpy's broadcast check and raises ``ValueError``.  Replicated, not fixed
+    (SURVEY.md 7.3-H5); pinned by the live-reference fixture tests/golden/ref_hybrid_axis.npz."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("ek_thermo.vertical: t and q must be torch CUDA tensors (no CPU path)")
+    a_len = len(A)
+    nlev_t, nlev = int(t.shape[vertical_axis]), a_len - 1
+    levels = None if nlev_t == nlev else list(range(nlev - nlev_t + 1, nlev + 1))  # V:1191-1203
+    alpha, delta = pressure_on_hybrid_levels(A, B, sp, alpha_top=alpha_top, levels=levels, output=("alpha", "delta"))
+    return _column_kernel(t, q, 0, vertical_axis, alpha=alpha, delta=delta)  # moves t, q, alpha and delta alike (V:981-986)
+
+
+def _height_form(dphi, zs, mode):
+    """Output form `mode` of a thickness already in memory, with numpy's broadcasting of zs (and its ValueError)."""
+    zs_t = torch.as_tensor(zs, dtype=None if isinstance(zs, torch.Tensor) else dphi.dtype, device=dphi.device)
+    try:
+        torch.broadcast_shapes(tuple(dphi.shape), tuple(zs_t.shape))
+    except RuntimeError:
+        raise ValueError(f"operands could not be broadcast together with shapes {tuple(dphi.shape)} {tuple(zs_t.shape)}") from None
+    return _b.execute("height_from_thickness", (dphi, zs_t), (mode,))
+
+
+def geopotential_height_from_geopotential(z):
+    """z / g.  Reference V:330-353."""
+    return _b.execute("height_from_thickness", (z, 0.0), (3,))
+
+
+def geometric_height_from_geopotential(z):
+    """R z/g / (R - z/g) with the reference's Earth radius.  Reference V:472-502."""
+    return _b.execute("height_from_thickness", (z, 0.0), (6,))
+
+
 def relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp, alpha_top="ifs", vertical_axis=0):
     """Same, with alpha/delta computed inside the kernel from sp and A/B (never materialised).  Reference V:894-994.
 
-    ``t``/``q`` may hold only the bottom-most contiguous levels of the model (V:1191-1203)."""
+    ``t``/``q`` may hold only the bottom-most contiguous levels of the model (V:1191-1203).  ``vertical_axis != 0`` behaves as
+    in the reference (see ``_thickness_axis_as_reference``)."""
+    if vertical_axis != 0:
+        return _thickness_axis_as_reference(t, q, A, B, sp, alpha_top, vertical_axis)
     return _column_kernel(t, q, 0, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top)
 
 
 def geopotential_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", vertical_axis=0):
     """Geopotential on the full levels: thickness + surface geopotential, one kernel.  Reference V:997-1069."""
+    if vertical_axis != 0:
+        return _height_form(_thickness_axis_as_reference(t, q, A, B, sp, alpha_top, vertical_axis), zs, 1)
     return _column_kernel(t, q, 1, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top, zs=zs)
 
 
@@ -213,4 +256,6 @@ def height_on_hybrid_levels(t, q, zs, A, B, sp, alpha_top="ifs", h_type="geometr
     if h_reference not in ["sea", "ground"]:
         raise ValueError(f"Unknown '{h_reference=}'. Use 'sea' or 'ground'.")  # V:1163-1164
     mode = _HM[("geometric" if h_type == "geometric" else "geopotential", h_reference)]  # any other h_type -> geopotential (V:1175-1186)
+    if vertical_axis != 0:
+        return _height_form(_thickness_axis_as_reference(t, q, A, B, sp, alpha_top, vertical_axis), zs, mode)
     return _column_kernel(t, q, mode, vertical_axis, sp=sp, A=A, B=B, alpha_top=alpha_top, zs=zs)

@@ -189,6 +189,10 @@ enum { EK_HM_THICKNESS = 0, EK_HM_GEOPOTENTIAL = 1, EK_HM_GH_SEA = 2, EK_HM_GH_G
 EK_THERMO_FN(geopotential_on_hybrid_levels, const void* t, const void* q, int nlev, int64_t npl, const void* sp, const void* A,
              const void* B, int nhalf, int top_toa, double alpha_top, const void* alpha, const void* delta, const void* zs, int mode,
              void* out, void* stream)
+/* the output forms of the function above, elementwise, for a thickness / geopotential that is already in memory: mode 0-5 as
+ * EK_HM_* (dphi = thickness, zs = surface geopotential), 6 = geometric_height_from_geopotential(dphi) (V:472-502); mode 3 with
+ * dphi = z is geopotential_height_from_geopotential(z) (V:330-353).  Used by the replicated vertical_axis != 0 path. */
+EK_THERMO_FN(height_from_thickness, ek_operand dphi, ek_operand zs, int mode, void* out, int64_t n, void* stream)
 /* the (t, q, p) suite with p = full-level pressure computed in registers from sp and A/B (nlev + 1 coefficients each);
  * t, q and every output are [nlev, npl]; p_out (optional) receives the pressure itself */
 EK_THERMO_FN(suite_tq_hybrid, const void* t, const void* q, const void* sp, const void* A, const void* B, int nlev, int64_t npl,

@@ -166,6 +166,68 @@ def pack_hybrid():
     return blob, mism
 
 
+def pack_hybrid_axis():
+    """vertical_axis != 0 in the geopotential functions (reference vertical.py:981-986): the reference moves the alpha / delta
+    it just computed with their level axis FIRST a second time, which is only shape-consistent for square fields (as many columns
+    as levels) and scrambles alpha / delta there; every other shape raises numpy's broadcast ValueError.  SURVEY 7.3-H5 is
+    "replicate, don't fix": these are the reference's own outputs for a square field, and the exception it raises otherwise.
+    Also the stand-alone height conversions (vertical.py:330-502) that the replicated path post-processes with."""
+    sys.path.insert(0, os.path.join(REF, "tests", "vertical"))
+    import _hybrid_core_data as D
+    import vertical_oracle as voracle
+    from earthkit.meteo import vertical as ref_vertical
+
+    rng = np.random.default_rng(29)
+    A, B = np.asarray(D.A, dtype=np.float64), np.asarray(D.B, dtype=np.float64)
+    n = 12  # 12 bottom-most levels x 12 columns
+    sp = rng.uniform(6.0e4, 1.05e5, n)
+    zs = rng.uniform(-300.0, 2.0e4, n)
+    pf = ref_vertical.pressure_on_hybrid_levels(A, B, sp, levels=list(range(A.size - n, A.size)))
+    t = np.clip(288.15 * (pf / 101325.0) ** 0.19 + rng.uniform(-8, 8, pf.shape), 180.0, 320.0)  # [level, column]
+    q = rng.uniform(1e-6, 0.02, pf.shape)
+    blob = {"A": A, "B": B, "sp": sp, "zs": zs, "t": t, "q": q}
+    mism = 0
+    t1, q1 = np.ascontiguousarray(t.T), np.ascontiguousarray(q.T)  # [column, level]: vertical axis 1
+    for axis in (1, -1):
+        calls = {"thickness": lambda m: m.relative_geopotential_thickness_on_hybrid_levels(t1, q1, A, B, sp, vertical_axis=axis),
+                 "geopotential": lambda m: m.geopotential_on_hybrid_levels(t1, q1, zs, A, B, sp, vertical_axis=axis)}
+        for ht in ("geometric", "geopotential"):
+            for hr in ("sea", "ground"):
+                calls[f"h_{ht}_{hr}"] = (lambda m, ht=ht, hr=hr: m.height_on_hybrid_levels(t1, q1, zs, A, B, sp, h_type=ht, h_reference=hr, vertical_axis=axis))
+        for name, fn in calls.items():
+            rv, ov = fn(ref_vertical), fn(voracle)
+            blob[f"axis{axis}/{name}"] = rv
+            mism += int(not (rv.shape == ov.shape and np.array_equal(rv, ov, equal_nan=True)))
+    # the consistent answer (vertical axis first), to show that the reference's axis != 0 result is NOT it
+    blob["axis0/thickness"] = ref_vertical.relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp)
+    try:  # any non-square field
+        ref_vertical.relative_geopotential_thickness_on_hybrid_levels(t1[:5], q1[:5], A, B, sp[:5], vertical_axis=1)
+        blob["nonsquare_error"] = np.asarray("none")
+    except Exception as e:  # noqa: BLE001
+        blob["nonsquare_error"] = np.asarray(type(e).__name__)
+    z = np.concatenate([rng.uniform(-5.0e3, 6.0e5, 200), [0.0, np.nan, np.inf, -np.inf, 6371229.0 * 9.80665]])
+    blob["conv/z"] = z
+    with np.errstate(all="ignore"):
+        blob["conv/geopotential_height"] = ref_vertical.geopotential_height_from_geopotential(z)
+        blob["conv/geometric_height"] = ref_vertical.geometric_height_from_geopotential(z)
+        mism += int(not np.array_equal(blob["conv/geopotential_height"], voracle.geopotential_height_from_geopotential(z), equal_nan=True))
+        mism += int(not np.array_equal(blob["conv/geometric_height"], voracle.geometric_height_from_geopotential(z), equal_nan=True))
+    return blob, mism
+
+
+def main_hybrid_axis():
+    blob, mism = pack_hybrid_axis()
+    np.savez_compressed(os.path.join(HERE, "ref_hybrid_axis.npz"), **blob)
+    path = os.path.join(HERE, "PINNING.json")
+    with open(path) as f:
+        pin = json.load(f)
+    pin["hybrid_axis"] = {"arrays_not_bit_identical_to_reference": mism, "n_arrays": sum(k.startswith(("axis", "conv/g")) for k in blob),
+                          "nonsquare_error": str(blob["nonsquare_error"])}
+    with open(path, "w") as f:
+        json.dump(pin, f, indent=1, sort_keys=True)
+    print(json.dumps(pin["hybrid_axis"]))
+
+
 WIND_CASES = [  # (function, argument names, kwargs)
     ("speed", ("u", "v"), {}),
     ("direction", ("u", "v"), {"convention": "meteo"}),
@@ -267,4 +329,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--hybrid-axis" in sys.argv:  # only the vertical_axis != 0 fixtures (added in round 2; the other files stay as generated)
+        main_hybrid_axis()
+    else:
+        main()
+        main_hybrid_axis()

@@ -194,12 +194,43 @@ def test_geopotential_against_oracle(hyb, shape):
         got = geo_call(vertical, name, dt_, dq, dzs, a, b, dsp, "ifs")
         want = geo_call(voracle, name, t, q, zs, a, b, sp, "ifs")
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-12, atol=1e-7, err_msg=name)
-    # vertical axis last (the sensible meaning; the reference's own moveaxis of alpha/delta is only consistent for axis 0)
-    thick = vertical.relative_geopotential_thickness_on_hybrid_levels(dt_, dq, a, b, dsp)
-    last = vertical.relative_geopotential_thickness_on_hybrid_levels(dt_.movedim(0, -1).contiguous(), dq.movedim(0, -1).contiguous(), a, b, dsp,
-                                                                     vertical_axis=-1)
-    torch.testing.assert_close(last.movedim(-1, 0), thick, rtol=0, atol=0)
     # identities: geopotential = thickness + zs; thickness decreases towards the surface and is positive
     geo = vertical.geopotential_on_hybrid_levels(dt_, dq, dzs, a, b, dsp)
     torch.testing.assert_close(geo, thick + dzs, rtol=1e-15, atol=1e-9)
     assert bool((thick[:-1] > thick[1:]).all()) and bool((thick[-1] > 0).all())
+
+
+def test_vertical_axis_behaves_as_the_reference():
+    """vertical_axis != 0 ("replicate, don't fix"): the reference moves the alpha / delta it computed level-
+    axis-first a second time (V:981-986), so only square fields pass numpy's broadcast check -- with scrambled alpha / delta --
+    and every other shape raises ValueError.  The wrapper returns the reference's own numbers for the square field of the live
+    fixture (tests/golden/ref_hybrid_axis.npz, generated from the unmodified reference), which are NOT the axis-0 answer, and
+    raises ValueError otherwise; vertical axis 0 stays the consistent kernel path.  Also the two stand-alone height conversions."""
+    import os
+
+    from ek_thermo import vertical
+
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hybrid_axis.npz")) as z:
+        fx = {k: z[k] for k in z.files}
+    A, B = fx["A"], fx["B"]
+    d = {k: torch.from_numpy(fx[k]).to(DEV) for k in ("sp", "zs", "t", "q")}
+    t1, q1 = d["t"].T.contiguous(), d["q"].T.contiguous()  # [column, level]
+    for axis in (1, -1):
+        got = {"thickness": vertical.relative_geopotential_thickness_on_hybrid_levels(t1, q1, A, B, d["sp"], vertical_axis=axis),
+               "geopotential": vertical.geopotential_on_hybrid_levels(t1, q1, d["zs"], A, B, d["sp"], vertical_axis=axis)}
+        for ht in ("geometric", "geopotential"):
+            for hr in ("sea", "ground"):
+                got[f"h_{ht}_{hr}"] = vertical.height_on_hybrid_levels(t1, q1, d["zs"], A, B, d["sp"], h_type=ht, h_reference=hr, vertical_axis=axis)
+        for name, g in got.items():
+            np.testing.assert_allclose(g.cpu().numpy(), fx[f"axis{axis}/{name}"], rtol=1e-12, atol=1e-7, err_msg=f"axis {axis} {name}")
+    consistent = vertical.relative_geopotential_thickness_on_hybrid_levels(d["t"], d["q"], A, B, d["sp"])
+    np.testing.assert_allclose(consistent.cpu().numpy(), fx["axis0/thickness"], rtol=1e-12, atol=1e-7)
+    assert not np.allclose(fx["axis1/thickness"].T, fx["axis0/thickness"], rtol=1e-3)  # the reference's axis-1 result is not the axis-0 one
+    assert str(fx["nonsquare_error"]) == "ValueError"
+    with pytest.raises(ValueError):
+        vertical.relative_geopotential_thickness_on_hybrid_levels(t1[:5], q1[:5], A, B, d["sp"][:5], vertical_axis=1)
+    with pytest.raises(ValueError):
+        vertical.height_on_hybrid_levels(t1[:5], q1[:5], d["zs"][:5], A, B, d["sp"][:5], vertical_axis=-1)
+    zz = torch.from_numpy(fx["conv/z"]).to(DEV)
+    np.testing.assert_allclose(vertical.geopotential_height_from_geopotential(zz).cpu().numpy(), fx["conv/geopotential_height"], rtol=1e-15, equal_nan=True)
+    np.testing.assert_allclose(vertical.geometric_height_from_geopotential(zz).cpu().numpy(), fx["conv/geometric_height"], rtol=1e-12, equal_nan=True)

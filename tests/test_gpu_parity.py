@@ -805,6 +805,63 @@ def test_host_array_staged_pipeline_equals_device_path(ek):
         host.release_staging()
 
 
+def test_host_functions_under_apply_ufunc_semantics(ek):
+    """the reference's own high-level idiom is ``xr.apply_ufunc(potential_temperature, t, p)`` (reference
+    tests/vertical/test_xr_theta.py:34).  xarray is not in this image, so the test hands ``host.thermo`` exactly what
+    apply_ufunc hands a function, with plain numpy stand-ins: the ``.data`` of DataArrays as read-only arrays (netCDF-backed
+    variables), non-contiguous views (after ``transpose`` / ``isel``), broadcast dimensions of length 1, float32 variables,
+    0-d arrays (a reduced dimension), per-element calls (``vectorize=True``: numpy scalars in, one value out), and
+    ``dask="parallelized"`` blocks mapped from a thread pool.  Results: a NEW array of the broadcast shape and the input
+    dtype, inputs untouched, values those of the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from ek_thermo import host
+
+    rng = np.random.default_rng(77)
+    lev, lat, lon = 7, 37, 53
+    t = rng.uniform(210.0, 310.0, (lev, lat, lon))
+    p = rng.uniform(2.0e4, 1.02e5, (lev, lat, lon))
+    q = rng.uniform(1e-6, 0.015, (lev, lat, lon))
+    want = oracle.potential_temperature(t, p)
+    fn = host.thermo.potential_temperature
+    # read-only .data (a variable opened from a file), result is a fresh writable array
+    t_ro, p_ro = t.copy(), p.copy()
+    t_ro.flags.writeable = False
+    p_ro.flags.writeable = False
+    got = fn(t_ro, p_ro)
+    assert got.shape == t.shape and got.dtype == np.float64 and got.flags.writeable and not np.shares_memory(got, t_ro)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert np.array_equal(t_ro, t) and np.array_equal(p_ro, p)
+    # non-contiguous views: transposed (lat, lon, lev) and strided selections
+    got = fn(np.transpose(t, (1, 2, 0)), np.transpose(p, (1, 2, 0)))
+    np.testing.assert_allclose(got, np.transpose(want, (1, 2, 0)), rtol=1e-12)
+    np.testing.assert_allclose(fn(t[::2, 3:, ::5], p[::2, 3:, ::5]), want[::2, 3:, ::5], rtol=1e-12)
+    # a pressure coordinate broadcast against the field: (lev, 1, 1) with (lev, lat, lon), and the other way round
+    p_lev = np.linspace(2.0e4, 1.0e5, lev).reshape(lev, 1, 1)
+    np.testing.assert_allclose(fn(t, p_lev), oracle.potential_temperature(t, p_lev), rtol=1e-12)
+    np.testing.assert_allclose(fn(t[:, :1, :1], p), oracle.potential_temperature(t[:, :1, :1], p), rtol=1e-12)
+    # float32 variables stay float32; a float32 field with a float64 coordinate promotes like numpy
+    t32, p32 = t.astype(np.float32), p.astype(np.float32)
+    g32 = fn(t32, p32)
+    assert g32.dtype == np.float32
+    np.testing.assert_allclose(g32, oracle.potential_temperature(t32, p32), rtol=1e-5)
+    assert fn(t32, p_lev).dtype == np.float64
+    # 0-d arrays and numpy scalars (vectorize=True calls the function once per element)
+    s0 = fn(np.asarray(t[0, 0, 0]), np.asarray(p[0, 0, 0]))
+    assert np.ndim(s0) == 0 and abs(float(s0) - float(want[0, 0, 0])) <= 1e-12 * float(want[0, 0, 0])
+    vec = np.vectorize(fn)(t[0, :3, :4], p[0, :3, :4])
+    np.testing.assert_allclose(vec, want[0, :3, :4], rtol=1e-12)
+    # dask="parallelized": blocks along the first dimension evaluated from a thread pool, concatenated by the caller
+    with ThreadPoolExecutor(4) as pool:
+        blocks = list(pool.map(lambda k: host.thermo.relative_humidity_from_specific_humidity(t[k], q[k], p[k]), range(lev)))
+    np.testing.assert_allclose(np.stack(blocks), oracle.relative_humidity_from_specific_humidity(t, q, p), rtol=1e-12)
+    # keyword options and multiple outputs pass through (apply_ufunc(..., kwargs=..., output_core_dims=[[], []]))
+    tl, pl = host.thermo.lcl(t, t - 4.0, p, method="bolton")
+    wl = oracle.lcl(t, t - 4.0, p, method="bolton")
+    np.testing.assert_allclose(tl, wl[0], rtol=1e-12)
+    np.testing.assert_allclose(pl, wl[1], rtol=1e-12)
+
+
 def test_host_array_pipeline_is_reentrant(ek):
     """dask's threaded scheduler and xr.apply_ufunc call the host functions from several threads at once: every running
     call owns its staging buffers (checked out under a lock), so concurrent calls -- and a release_staging() in the middle

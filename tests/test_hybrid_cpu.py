@@ -2,6 +2,7 @@
 live-reference fixtures; the per-point formulas the kernels use (g++ build) against the oracle; the wrapper's
 argument errors."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -174,3 +175,25 @@ def test_geopotential_wrapper_errors(monkeypatch):
         vertical.relative_geopotential_thickness_on_hybrid_levels(t, t, a, b, t[0], alpha_top="nope")
     with pytest.raises(ValueError):
         vertical.relative_geopotential_thickness_on_hybrid_levels_from_alpha_delta(t, t, t[:2], t[:2])
+
+
+def test_oracle_matches_reference_for_vertical_axis_not_zero():
+    """The live-reference fixture of the vertical_axis != 0 behaviour (reference vertical.py:981-986; generated by
+    tests/golden/make_golden.py --hybrid-axis): the oracle reproduces the reference's numbers bit for bit, raises where it
+    raises, and PINNING.json records the comparison made at generation time."""
+    import json
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with np.load(os.path.join(here, "golden", "ref_hybrid_axis.npz")) as z:
+        fx = {k: z[k] for k in z.files}
+    A, B, sp, zs = fx["A"], fx["B"], fx["sp"], fx["zs"]
+    t1, q1 = np.ascontiguousarray(fx["t"].T), np.ascontiguousarray(fx["q"].T)
+    for axis in (1, -1):
+        np.testing.assert_array_equal(voracle.relative_geopotential_thickness_on_hybrid_levels(t1, q1, A, B, sp, vertical_axis=axis), fx[f"axis{axis}/thickness"])
+        np.testing.assert_array_equal(voracle.geopotential_on_hybrid_levels(t1, q1, zs, A, B, sp, vertical_axis=axis), fx[f"axis{axis}/geopotential"])
+        np.testing.assert_array_equal(voracle.height_on_hybrid_levels(t1, q1, zs, A, B, sp, vertical_axis=axis), fx[f"axis{axis}/h_geometric_ground"])
+    with pytest.raises(ValueError):
+        voracle.relative_geopotential_thickness_on_hybrid_levels(t1[:5], q1[:5], A, B, sp[:5], vertical_axis=1)
+    with open(os.path.join(here, "golden", "PINNING.json")) as f:
+        pin = json.load(f)["hybrid_axis"]
+    assert pin["arrays_not_bit_identical_to_reference"] == 0 and pin["nonsquare_error"] == "ValueError"
