@@ -195,6 +195,7 @@ def test_geopotential_against_oracle(hyb, shape):
         want = geo_call(voracle, name, t, q, zs, a, b, sp, "ifs")
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-12, atol=1e-7, err_msg=name)
     # identities: geopotential = thickness + zs; thickness decreases towards the surface and is positive
+    thick = vertical.relative_geopotential_thickness_on_hybrid_levels(dt_, dq, a, b, dsp)
     geo = vertical.geopotential_on_hybrid_levels(dt_, dq, dzs, a, b, dsp)
     torch.testing.assert_close(geo, thick + dzs, rtol=1e-15, atol=1e-9)
     assert bool((thick[:-1] > thick[1:]).all()) and bool((thick[-1] > 0).all())
