@@ -634,7 +634,7 @@ def run_e2e(args, wl, arrays, hyb, out, n_slabs, device, world, barrier, max_ove
 
     el = timed(call)
     e2e = {"value": world * steps * n_e2e / el, "unit": "grid-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(outputs) * esz * n_e2e,
-           "steps": steps, "step_seconds_rank0": list(per_step), "pcie_gbs": (h2d + len(outputs) * esz * n_e2e) * steps / el / 1e9,
+           "steps": steps, "step_seconds_rank0": list(per_step), "pcie_gbs_all_gpus": world * (h2d + len(outputs) * esz * n_e2e) * steps / el / 1e9,
            "sample": f"{lv} of {n_slabs} level slabs per step ({n_e2e} points) through ek_thermo.hostpipe.HostSuite, page-locked host buffers"}
     # the device result of the timed steps and the host-pipeline result agree bit for bit on the shared slab
     name0 = outputs[0]
