@@ -30,7 +30,8 @@ n = npl * nlev
 kernels = {
     # name: (callable, algorithmic bytes per [level, point] element)
     "pressure full": (lambda: vertical.pressure_on_hybrid_levels(A, B, sp), esz * (1 + 1 / nlev)),
-    "pressure full+half+delta+alpha": (lambda: vertical.pressure_on_hybrid_levels(A, B, sp, output=("full", "half", "delta", "alpha")), esz * (4 + 2 / nlev)),
+    # delta and alpha are float64 arrays whatever the dtype of sp (as in the reference)
+    "pressure full+half+delta+alpha": (lambda: vertical.pressure_on_hybrid_levels(A, B, sp, output=("full", "half", "delta", "alpha")), esz * (2 + 2 / nlev) + 16),
     "thickness (alpha/delta in registers)": (lambda: vertical.relative_geopotential_thickness_on_hybrid_levels(t, q, A, B, sp), esz * (3 + 1 / nlev)),
     "geometric height above ground": (lambda: vertical.height_on_hybrid_levels(t, q, zs, A, B, sp), esz * (3 + 2 / nlev)),
     "suite_tq_hybrid (5 outputs)": (lambda: fused.suite_tq_hybrid(t, q, sp, A, B), esz * (7 + 1 / nlev)),
