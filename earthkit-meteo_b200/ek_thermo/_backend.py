@@ -377,8 +377,13 @@ def execute_suite_batch(symbol: str, seg_args, out_names, slots, outs=None, ept_
     res = [dict() for _ in range(n_seg)]
     if n_seg == 0:
         return res
+    for a in lists:
+        for t in a:
+            if not isinstance(t, torch.Tensor):
+                raise TypeError("ek_thermo: batched suite arguments are lists of torch CUDA tensors or Python numbers")
+    dev = _check_device([t for a in lists for t in a])  # every field a CUDA tensor on one device: no CPU path
     first = lists[0][0]
-    dtype, dev, shape = first.dtype, first.device, first.shape
+    dtype, shape = first.dtype, first.shape
     if dtype not in _SUFFIX:
         raise TypeError("ek_thermo: batched suites take float64 or float32 tensors")
     keep = []
@@ -387,9 +392,7 @@ def execute_suite_batch(symbol: str, seg_args, out_names, slots, outs=None, ept_
     for k, a in enumerate(seg_args):
         if isinstance(a, (list, tuple)):
             for t in a:
-                if not isinstance(t, torch.Tensor) or not t.is_cuda:
-                    raise TypeError("ek_thermo: got a non-CUDA tensor. This package only runs on CUDA tensors (no CPU fallback)")
-                if t.dtype != dtype or t.device != dev or t.shape != shape or not t.is_contiguous():
+                if t.dtype != dtype or t.shape != shape or not t.is_contiguous():
                     raise ValueError("ek_thermo: the fields of a batched suite must share dtype, device and shape and be contiguous")
             arr = (c_void_p * n_seg)(*[t.data_ptr() for t in a])
             keep.append(arr)

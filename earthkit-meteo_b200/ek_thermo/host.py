@@ -150,6 +150,7 @@ _STAGE_LAG = 1          # (pageable results) a chunk is copied out of staging th
 _STAGE_WORKERS = 12     # upper bound; never more than the CPUs this process may run on
 _PINNED_RESULTS = True
 _pool = None
+_pool_size = 0
 _lock = threading.Lock()
 _free_sets = []   # _StagingSet objects no call is using
 _generation = 0   # bumped by release_staging(): sets of an older generation are dropped when their call returns
@@ -186,13 +187,14 @@ def _checkin(s):
 
 
 def _workers():
-    global _pool
+    global _pool, _pool_size
     with _lock:
         if _pool is None:
             import os
             from concurrent.futures import ThreadPoolExecutor
 
-            _pool = ThreadPoolExecutor(max_workers=max(2, min(_STAGE_WORKERS, len(os.sched_getaffinity(0)))), thread_name_prefix="ek_host")
+            _pool_size = max(2, min(_STAGE_WORKERS, len(os.sched_getaffinity(0))))
+            _pool = ThreadPoolExecutor(max_workers=_pool_size, thread_name_prefix="ek_host")
         return _pool
 
 
@@ -249,7 +251,7 @@ def _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device):
     n_pageable = sum(1 for x in pinned if not x)
     # every array's chunk is copied in pieces by several workers at once: one memcpy stream per array (3 for a suite) leaves
     # most of the host's memory bandwidth unused and makes the staging step the bottleneck of the whole pipeline
-    parts = max(1, min(4, pool._max_workers // max(1, n_pageable)))
+    parts = max(1, min(4, _pool_size // max(1, n_pageable)))
 
     def fill(ci):
         """Worker threads copy chunk ci of every pageable input into the slot's staging buffers."""
@@ -272,7 +274,7 @@ def _pipeline_staged_run(st_set, fn, args, kwargs, put, flat, dt, n, device):
     def copy_out(slot):
         b, e = ranges[slot]
         events[slot].synchronize()
-        step = -(-(e - b) // max(1, min(4, pool._max_workers // max(1, nres))))
+        step = -(-(e - b) // max(1, min(4, _pool_size // max(1, nres))))
         pending[slot] = [pool.submit(np.copyto, outs[j][b + o:min(e, b + o + step)], st_set.buf(dt, slot, "out", j).numpy()[o:min(e - b, o + step)])
                          for j in range(nres) for o in range(0, e - b, step)]
 

@@ -55,6 +55,18 @@ def _run(op, dtype, operands, outs, n, opt0=0, opt1=0, eps=1e-4, mask=1, m=0, tm
 def fake_call(symbol, dtype, device, c_args):
     from ek_thermo import _backend as b
 
+    if symbol in ("suite_tqp_batch", "suite_ttdp_batch"):  # one mock "launch" per field: the per-field operands are read back from the pointer tables
+        n_seg, pa, pb, pc, scalars, out_tab, mask, em, n = c_args
+        mask = _val(mask)
+        base = symbol[:-len("_batch")]
+        for j in range(_val(n_seg)):
+            ops = []
+            for k, tab in enumerate((pa, pb, pc)):
+                tab = _val(tab)
+                ops.append(b.ek_operand(ctypes.cast(tab, ctypes.POINTER(c_void_p))[j], 0.0) if tab else b.ek_operand(None, scalars[k]))
+            o = [ctypes.cast(out_tab[k], ctypes.POINTER(c_void_p))[j] if (mask >> k) & 1 else None for k in range(b.N_SUITE_SLOTS)]
+            _run(base, dtype, ops, o, _val(n), mask=mask, m=_val(em))
+        return None
     if symbol in ("suite_tqp", "suite_ttdp"):
         operands, (outs, mask, em, n) = c_args[:3], c_args[3:]
         mask = _val(mask)

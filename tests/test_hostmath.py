@@ -108,3 +108,34 @@ def test_fused_suite_functors_match_oracle(monkeypatch, suite, ept_method, dtype
             assert np.quantile(rel, 0.995 if dtype == np.float32 else 1.0) <= rtol, (name, outputs, rel.max())
     with pytest.raises(KeyError):
         fn(*a_t, outputs=("ept",), ept_method="nope")
+
+
+def test_batched_suite_host_logic(monkeypatch):
+    """fused.suite_tqp_batch / suite_ttdp_batch on the mock device: the pointer tables, the broadcast scalar, preallocated outputs
+    and the argument checks of the Python side (the CUDA kernel itself is covered by the GPU test of the same name)."""
+    from ek_thermo import fused
+
+    hostmath_backend.install(monkeypatch)
+    inp = random_inputs(4 * 500, seed=3)
+    ts, qs, tds, ps = ([torch.from_numpy(inp[k][j * 500:(j + 1) * 500].copy()) for j in range(4)] for k in ("t", "q", "td", "p"))
+    got = fused.suite_tqp_batch(ts, qs, ps, outputs=("theta", "rh", "ept"), ept_method="bolton35")
+    assert len(got) == 4
+    for j in range(4):
+        want = fused.suite_tqp(ts[j], qs[j], ps[j], outputs=("theta", "rh", "ept"), ept_method="bolton35")
+        for name in want:
+            assert torch.equal(torch.nan_to_num(got[j][name]), torch.nan_to_num(want[name])), (j, name)
+    pre = [{"q": torch.empty_like(ts[0])} for _ in range(4)]
+    got = fused.suite_ttdp_batch(ts, tds, 85000.0, outputs=("q", "wbpt"), out=pre)
+    for j in range(4):
+        assert got[j]["q"].data_ptr() == pre[j]["q"].data_ptr()
+        want = fused.suite_ttdp(ts[j], tds[j], 85000.0, outputs=("q", "wbpt"))
+        assert torch.equal(torch.nan_to_num(got[j]["wbpt"]), torch.nan_to_num(want["wbpt"]))
+    assert fused.suite_tqp_batch([], [], []) == []
+    with pytest.raises(ValueError):
+        fused.suite_tqp_batch(ts, qs[:3], ps)
+    with pytest.raises(ValueError):
+        fused.suite_tqp_batch(ts, qs, [p[:10] for p in ps])
+    with pytest.raises(TypeError):
+        fused.suite_tqp_batch(1.0, 2.0, 3.0)
+    with pytest.raises(KeyError):
+        fused.suite_tqp_batch(ts, qs, ps, outputs=("ept",), ept_method="nope")

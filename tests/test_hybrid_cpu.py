@@ -197,3 +197,17 @@ def test_oracle_matches_reference_for_vertical_axis_not_zero():
     with open(os.path.join(here, "golden", "PINNING.json")) as f:
         pin = json.load(f)["hybrid_axis"]
     assert pin["arrays_not_bit_identical_to_reference"] == 0 and pin["nonsquare_error"] == "ValueError"
+
+
+def test_working_dtype_follows_numpy_promotion():
+    """ek_thermo.vertical computes in the dtype numpy's promotion gives the reference (V:630-663): a float64 operand among
+    float32 ones promotes, Python lists count as float64 arrays, Python numbers are weak, integers become float64."""
+    from ek_thermo import vertical
+
+    f32, f64 = torch.zeros(3, dtype=torch.float32), torch.zeros(3, dtype=torch.float64)
+    wd = vertical._working_dtype
+    assert wd(f32, f32) == torch.float32 and wd(f32, f64) == torch.float64 and wd(f64) == torch.float64
+    assert wd(f32, np.zeros(3, dtype=np.float32)) == torch.float32 and wd(f32, np.zeros(3)) == torch.float64
+    assert wd(f32, [0.0, 1.0]) == torch.float64  # xp.asarray([...]) is a float64 array
+    assert wd(f32, 1.0, 2, None) == torch.float32  # Python scalars do not promote (numpy 2)
+    assert wd(torch.zeros(3, dtype=torch.int32)) == torch.float64 and wd(torch.zeros(3, dtype=torch.float16)) == torch.float32
