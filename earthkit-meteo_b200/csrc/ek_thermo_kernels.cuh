@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
     const int64_t tiles_per_seg = n_per_seg / TILE;
     const int64_t ntiles = tiles_per_seg * B.n_seg;
     const int64_t toff = (int64_t)threadIdx.x * Vec16<T>::N;
+    const bool all_arrays = B.in_mask == (1u << NIN) - 1u;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int seg = (int)(tile / tiles_per_seg);
         const int64_t base = (tile - (int64_t)seg * tiles_per_seg) * TILE + toff;
@@ -459,13 +460,26 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) out.p[o] = ((B.out_mask >> o) & 1u) ? B.out[o][seg] : nullptr;
         TileRegs<Op, T, UNROLL> A;
-        if (vec_ok) {
+        if (vec_ok && all_arrays)
+            load_tile<Op, T, UNROLL, true, true>(A, in, base);
+        else if (vec_ok)
             load_tile<Op, T, UNROLL, true, false>(A, in, base);
-            compute_store_tile<Op, OpE, T, UNROLL, true>(A, out, base, P, B.in_mask);
-        } else {
+        else
             load_tile<Op, T, UNROLL, false, false>(A, in, base);
-            compute_store_tile<Op, OpE, T, UNROLL, false>(A, out, base, P, B.in_mask);
+        if (Op::PREFETCH_NEXT) {  // the CTA's tile EK_PF_DIST rounds ahead, possibly in a later segment
+            const int64_t nt = tile + EK_PF_DIST * (int64_t)gridDim.x;
+            if (nt < ntiles) {
+                const int nseg = (int)(nt / tiles_per_seg);
+                InArgs<NIN> nin;
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) nin.p[k] = ((B.in_mask >> k) & 1u) ? B.in[k][nseg] : nullptr;
+                prefetch_tile_l2<Op, T, UNROLL>(nin, (nt - (int64_t)nseg * tiles_per_seg) * TILE + toff);
+            }
         }
+        if (vec_ok)
+            compute_store_tile<Op, OpE, T, UNROLL, true>(A, out, base, P, B.in_mask);
+        else
+            compute_store_tile<Op, OpE, T, UNROLL, false>(A, out, base, P, B.in_mask);
     }
     // tails: fewer than one tile of points per segment, one point per thread
     const int64_t tail = n_per_seg - tiles_per_seg * TILE;

@@ -58,6 +58,33 @@ with torch.cuda.stream(s):
         per_level()
 torch.cuda.synchronize()
 rows.append(("one launch per level, CUDA-graph replay", timed(g.replay)))
+# the levels are independent: captured on three forked streams, neighbouring launches overlap (one kernel's launch latency and
+# tail hide behind the next kernel's body) -- what a per-level caller with its own streams gets without the batched entry point
+side = [torch.cuda.Stream() for _ in range(3)]
+
+
+def per_level_streams():
+    main = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    for st in side:
+        st.wait_event(ev)
+    for k in range(nlev):
+        with torch.cuda.stream(side[k % 3]):
+            fused.suite_tqp(ts[k], qs[k], ps[k], outputs=outputs, out=outs[k])
+    for st in side:
+        e2 = torch.cuda.Event()
+        e2.record(st)
+        main.wait_event(e2)
+
+
+with torch.cuda.stream(s):
+    per_level_streams()
+    g3 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g3):
+        per_level_streams()
+torch.cuda.synchronize()
+rows.append(("per level on 3 streams, CUDA-graph replay", timed(g3.replay)))
 rows.append(("one batched launch over all levels", timed(batched)))
 print(f"theta + rh, {nlev} levels x {npl} points, {dtype}, {bpp} B/pt, roofline {bpp * npl / peak / 1e3:.2f} us per level")
 for name, ms in rows:
