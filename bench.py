@@ -335,9 +335,9 @@ _W = {}
 
 
 def _worker_run(args):
-    li, b, e = args
+    b, e = args
     with np.errstate(all="ignore"):
-        res = _W["fn"](*(x[li][b:e] for x in _W["arr"]))
+        res = _W["fn"](*(x[b:e] for x in _W["arr"]))
     return float(sum(np.nansum(r[:8]) for r in res))  # results stay in the worker (as they would stay in RAM)
 
 
@@ -363,27 +363,28 @@ def run_reference(args, wl):
     field, dev = cpu_field(kind, npl, levels, 0)
     lv = sample_levels(levels, 8)
     npd = np.float64 if dtype == "f64" else np.float32
-    per_level = [field.slabs_numpy([k], npd) for k in lv]
-    _W["arr"] = [[pl[i] for pl in per_level] for i in range(3)]
+    # one step = one slab of npl points made of equal parts of eight levels spread through the column (top, mixed-phase band,
+    # boundary layer): every step costs the same and represents the whole field, whatever --steps is
+    part = npl // len(lv)
+    pieces = [[x[:part] for x in field.slabs_numpy([k], npd)] for k in lv]
+    _W["arr"] = [np.ascontiguousarray(np.concatenate([pc[i] for pc in pieces])) for i in range(3)]
+    n_step = int(_W["arr"][0].size)
     _W["fn"] = cpu_step(kind, outputs, module)
-    del field
-    ctx = mp.get_context("fork")  # the workers inherit the input slabs and the imported reference; they never touch CUDA
+    del field, pieces
+    ctx = mp.get_context("fork")  # the workers inherit the input slab and the imported reference; they never touch CUDA
     with ctx.Pool(cores) as pool:
-        edges = np.linspace(0, npl, cores * 4 + 1).astype(np.int64)
-
-        def one_step(i):
-            li = i % len(lv)
-            pool.map(_worker_run, [(li, int(b), int(e)) for b, e in zip(edges[:-1], edges[1:])])
-
-        for i in range(max(args.warmup, 1)):
-            one_step(i)
+        edges = np.linspace(0, n_step, cores * 4 + 1).astype(np.int64)
+        chunks = [(int(b), int(e)) for b, e in zip(edges[:-1], edges[1:])]
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_worker_run, chunks)
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            one_step(i)
+        for _ in range(args.steps):
+            pool.map(_worker_run, chunks)
         el = time.perf_counter() - t0
+    npl = n_step
     value = args.steps * npl / el
     src = "unmodified reference (oracle/_ref, earthkit.meteo.thermo public functions)" if mkind == "reference" else "numpy oracle port of the reference"
-    sample = (f"{npl} points per step: one level slab of the workload's own field per step, cycling over levels {lv} "
+    sample = (f"{npl} points per step: {part} points from each of the levels {lv} of the workload's own field "
               f"(generated on {dev}, seed 0, same generator as the GPU arm), {src}, {cores} processes")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "grid-points/s", "n_gpus": args.gpus, "steps": args.steps,
