@@ -29,6 +29,9 @@
 #ifndef EK_MAX_THREADS
 #define EK_MAX_THREADS 256
 #endif
+#ifndef EK_DEFER_TILE
+#define EK_DEFER_TILE 0
+#endif
 #ifndef EK_PF_DIST
 #define EK_PF_DIST 2  // tiles ahead of the current one that prefetch_tile_l2 asks L2 for (functors with PREFETCH_NEXT)
 #endif
@@ -214,7 +217,7 @@ template <class Op, class = void> struct MinCtasOf {
     static constexpr int value = EK_MIN_CTAS;
 };
 template <class Op> struct MinCtasOf<Op, decltype((void)Op::HEAVY)> {
-    static constexpr int value = Op::HEAVY ? EK_HEAVY_MIN_CTAS : EK_MIN_CTAS;
+    static constexpr int value = Op::HEAVY ? (Op::HEAVY > 1 ? Op::HEAVY : EK_HEAVY_MIN_CTAS) : EK_MIN_CTAS;  // HEAVY > 1: that many CTAs
 };
 
 // The inputs of one tile, per thread: UNROLL 16-byte vectors of every input array, in registers.
@@ -277,6 +280,56 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
     constexpr int NOUT = Op::NOUT;
     constexpr int VEC = Vec16<T>::N;
     constexpr int VSTRIDE = kThreads * VEC;
+#if EK_DEFER_TILE
+    if constexpr (DeferColdOf<Op>::value && EK_LEAN_DEVICE && !IsBatch<Op>::value) {
+        // experiment: ALL points of the tile (UNROLL x VEC) through the fast functor back to back, NaN checks afterwards
+        T res[UNROLL][VEC][NOUT];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                T a[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) a[k] = r.x[k][u][v];
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) res[u][v][o] = T(0);
+                Op::template apply<T>(a, res[u][v], P);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            T y[NOUT][VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if ((sizeof(T) == 8 || ColdF32<Op>::value) && __builtin_expect(any_nan<NOUT>(res[u][v]), 0)) {
+                    T a2[NIN], r2[NOUT];
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k) a2[k] = r.x[k][u][v];
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) r2[o] = res[u][v][o];
+                    cold_point<OpE, T>(a2, r2, P, array_mask);
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) res[u][v][o] = r2[o];
+                }
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) y[o][v] = res[u][v][o];
+            }
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+                const bool w = Op::STATIC_MASK ? (((Op::STATIC_MASK >> o) & 1u) != 0) : (out.p[o] != nullptr);
+                if (w) {
+                    T* dst = static_cast<T*>(out.p[o]) + base + u * VSTRIDE;
+                    if (VECOK) {
+                        Vec16<T>::store(dst, y[o]);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) __stcs(dst + v, y[o][v]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         T y[NOUT][VEC];
