@@ -197,6 +197,87 @@ __device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek
 
 __device__ __forceinline__ double log_p0_over(double x) { return kRed[6] - log_(x); }
 
+// ---- sin / cos / atan2 for the wind functions ---------------------------------------------------------
+// Same contract as the primitives above: branch-free, ~1 ulp inside a fast domain, NaN outside it (the kernel then recomputes the
+// point with libdevice).  sincos_: |x| < 2^19, three-part Cody-Waite reduction by pi/2 (33 + 33 + 33 bits: exact products for
+// |k| < 2^20) and the fdlibm kernel polynomials.  atan2_: both arguments finite, normal and non-zero; atan on [0, 1] by fdlibm's
+// two break points (7/16, 11/16) and its degree-11 polynomial in w^2: two reciprocals and 11 FMAs instead of libdevice's ~100
+// instructions (the 24 B/pt direction kernel was issue-bound at 0.75 of the roofline).
+__constant__ double kTrig[22] = {
+    6.36619772367581382433e-01 /*2/pi*/, 1.57079632673412561417e+00 /*pio2_1*/, 6.07710050630396597660e-11 /*pio2_2*/, 2.02226624871116645580e-21 /*pio2_3*/,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06, -2.50507602534068634195e-08,
+    1.58969099521155010221e-10,  // S1..S6 (indices 4..9)
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07, 2.08757232129817482790e-09,
+    -1.13596475577881948265e-11,  // C1..C6 (10..15)
+    4.63647609000806093515e-01 /*atan(1/2) hi*/, 2.26987774529616870924e-17 /*lo*/, 7.85398163397448278999e-01 /*pi/4 hi*/, 3.06161699786838301793e-17 /*lo*/,
+    1.57079632679489655800e+00 /*pi/2 hi*/, 6.12323399573676603587e-17 /*lo*/};
+__constant__ double kAtan[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,  -1.11111104054623557880e-01,
+                                 9.09088713343650656196e-02,  -7.69187620504482999495e-02, 6.66107313738753120669e-02,  -5.83357013379057348645e-02,
+                                 4.97687799461593236017e-02,  -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+
+__device__ __forceinline__ void sincos_(double x, double& s, double& c) {
+    const bool bad = (unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x41200000u;  // |x| >= 2^19, inf, NaN: answer NaN
+    const double t = fma(x, kTrig[0], 0x1.8p52);
+    const int q = __double2loint(t);
+    const double kd = t - 0x1.8p52;
+    double r = fma(kd, -kTrig[1], x);
+    r = fma(kd, -kTrig[2], r);
+    r = fma(kd, -kTrig[3], r);
+    const double r2 = r * r;
+    double ps = fma(r2, kTrig[9], kTrig[8]);
+    ps = fma(r2, ps, kTrig[7]);
+    ps = fma(r2, ps, kTrig[6]);
+    ps = fma(r2, ps, kTrig[5]);
+    ps = fma(r2, ps, kTrig[4]);
+    const double sn = fma(r * r2, ps, r);
+    double pc = fma(r2, kTrig[15], kTrig[14]);
+    pc = fma(r2, pc, kTrig[13]);
+    pc = fma(r2, pc, kTrig[12]);
+    pc = fma(r2, pc, kTrig[11]);
+    pc = fma(r2, pc, kTrig[10]);
+    const double cs = fma(r2 * r2, pc, fma(r2, -0.5, 1.0));
+    const double a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
+    const double nan = __hiloint2double(0x7ff80000, 0);
+    s = bad ? nan : ((q & 2) ? -a : a);
+    c = bad ? nan : (((q + 1) & 2) ? -b : b);
+}
+__device__ __forceinline__ double sin_(double x) {
+    double s, c;
+    sincos_(x, s, c);
+    return s;
+}
+
+__device__ __forceinline__ double atan2_(double y, double x) {
+    const int hx = __double2hiint(x) & 0x7fffffff, hy = __double2hiint(y) & 0x7fffffff;
+    // zero, denormal, tiny, huge, inf, NaN in either argument: answer NaN (2^-1007 <= |.| < 2^1009 is the fast domain)
+    const bool bad = (unsigned)(hx - 0x01000000) >= 0x7e000000u || (unsigned)(hy - 0x01000000) >= 0x7e000000u;
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const double z = mn * rcp_(mx);  // in [0, 1]
+    const bool m1 = z >= 0.4375, m2 = z >= 0.6875;
+    const double num = m2 ? z - 1.0 : (m1 ? fma(2.0, z, -1.0) : z);
+    const double den = m2 ? z + 1.0 : (m1 ? 2.0 + z : 1.0);
+    const double w = num * rcp_(den);
+    const double hi = m2 ? kTrig[18] : (m1 ? kTrig[16] : 0.0), lo = m2 ? kTrig[19] : (m1 ? kTrig[17] : 0.0);
+    const double w2 = w * w, w4 = w2 * w2;
+    double s1 = fma(w4, kAtan[10], kAtan[8]);
+    s1 = fma(w4, s1, kAtan[6]);
+    s1 = fma(w4, s1, kAtan[4]);
+    s1 = fma(w4, s1, kAtan[2]);
+    s1 = fma(w4, s1, kAtan[0]);
+    double s2 = fma(w4, kAtan[9], kAtan[7]);
+    s2 = fma(w4, s2, kAtan[5]);
+    s2 = fma(w4, s2, kAtan[3]);
+    s2 = fma(w4, s2, kAtan[1]);
+    const double p = fma(w2, s1, w4 * s2);           // w^2 s1 + w^4 s2
+    double r = hi - ((fma(w, p, -lo)) - w);          // atan(z) in [0, pi/4]
+    if (swap) r = (kTrig[20] - r) + kTrig[21];       // |y| > |x|: pi/2 - atan(|x|/|y|)
+    if (__double2hiint(x) < 0) r = (2.0 * kTrig[20] - r) + 2.0 * kTrig[21];  // x < 0: pi - r
+    r = __hiloint2double(__double2hiint(r) | (__double2hiint(y) & 0x80000000), __double2loint(r));  // the sign of y
+    return bad ? __hiloint2double(0x7ff80000, 0) : r;
+}
+
 // ---- bisection tree table (see t_on_ma_bisect_tab in ek_thermo_formulas.inc) -----------------------------------
 // The reference's moist-adiabat bisection (T:1055-1079) starts every point at T0 - 20 and moves by +-60, +-30, ... K:
 // after i steps the iterate is one of 2^i values that do not depend on the data.  {es_mixed(t), ln t} of the 4095
