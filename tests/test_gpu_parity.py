@@ -354,6 +354,50 @@ def test_single_pass_suite_equals_the_ept_kernels(ek, dtype, ept_method):
         fused.suite_tqp(d["t"], d["q"], d["p"], outputs=("ept",), ept_method="nope")  # as the reference (T:1026)
 
 
+@pytest.mark.parametrize("ept_method", ["ifs", "bolton35", "bolton39"])
+def test_suites_on_special_values_equal_the_single_functions(ek, ept_method):
+    """The special-value set (NaN, +-inf, 0, negative and subnormal inputs, band edges and their neighbours, p - e straddling the
+    NaN rule) through the ten-output suites: NaN positions and infinities are those of the single-function kernels -- which
+    test_cuda_matches_oracle_edge holds to the oracle -- and finite values agree with them to rounding (a point with a NaN in any
+    output is recomputed as a whole by the exact functor, so bits may differ there)."""
+    from ek_thermo import fused
+
+    with np.errstate(all="ignore"):
+        inp = edge_inputs(n=4099, seed=33)
+    d = {k: torch.from_numpy(np.ascontiguousarray(inp[k])).to(DEV) for k in ("t", "q", "td", "p")}
+    th = ek.thermo
+    singles_q = {
+        "theta": lambda: th.potential_temperature(d["t"], d["p"]), "es": lambda: th.saturation_vapour_pressure(d["t"]),
+        "rh": lambda: th.relative_humidity_from_specific_humidity(d["t"], d["q"], d["p"]),
+        "td": lambda: th.dewpoint_from_specific_humidity(d["q"], d["p"]), "tv": lambda: th.virtual_temperature(d["t"], d["q"]),
+        "w": lambda: th.mixing_ratio_from_specific_humidity(d["q"]), "e": lambda: th.vapour_pressure_from_specific_humidity(d["q"], d["p"]),
+        "thetav": lambda: th.virtual_potential_temperature(d["t"], d["q"], d["p"]),
+        "ept": lambda: th.ept_from_specific_humidity(d["t"], d["q"], d["p"], method=ept_method),
+        "wbpt": lambda: th.wet_bulb_potential_temperature_from_specific_humidity(d["t"], d["q"], d["p"], ept_method=ept_method),
+    }
+    q_td = th.specific_humidity_from_dewpoint(d["td"], d["p"])
+    singles_td = {
+        "theta": singles_q["theta"], "es": singles_q["es"], "rh": lambda: th.relative_humidity_from_dewpoint(d["t"], d["td"]),
+        "q": lambda: q_td, "tv": lambda: th.virtual_temperature(d["t"], q_td), "w": lambda: th.mixing_ratio_from_dewpoint(d["td"], d["p"]),
+        "e": lambda: th.saturation_vapour_pressure(d["td"], phase="water"),
+        "thetav": lambda: th.virtual_potential_temperature(d["t"], q_td, d["p"]),
+        "ept": lambda: th.ept_from_dewpoint(d["t"], d["td"], d["p"], method=ept_method),
+        "wbpt": lambda: th.wet_bulb_potential_temperature_from_dewpoint(d["t"], d["td"], d["p"], ept_method=ept_method),
+    }
+    for suite, hname, singles in ((fused.suite_tqp, "q", singles_q), (fused.suite_ttdp, "td", singles_td)):
+        for outputs in (tuple(singles), tuple(singles)[:5] + ("ept", "wbpt")):  # run-time mask and (ifs) the seven-output instantiation
+            got = suite(d["t"], d[hname], d["p"], outputs=outputs, ept_method=ept_method)
+            for name in outputs:
+                g, w = got[name], singles[name]()
+                assert torch.equal(torch.isnan(g), torch.isnan(w)), (hname, name)
+                inf = torch.isinf(g) | torch.isinf(w)
+                assert torch.equal(g[inf], w[inf]), (hname, name)
+                fin = torch.isfinite(g) & torch.isfinite(w)
+                tiny = (g[fin] - w[fin]).abs() <= 1e-300  # subnormal results
+                rel = (g[fin] - w[fin]).abs() / w[fin].abs().clamp_min(1e-300)
+                assert bool(((rel <= 1e-10) | tiny).all()), (hname, name, float(rel.max()))
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
 def test_host_pipelines_for_every_suite(ek, dtype):
     """The host-buffer entry points (page-locked numpy in, numpy out, chunked on three streams) for the suites with the ept /
