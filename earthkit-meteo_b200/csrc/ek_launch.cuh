@@ -129,7 +129,7 @@ int launch_batch(const char* what, int n_seg, const void* const* const* ins, con
         B.n_seg = n_seg - s0 < kBatchMaxSeg ? n_seg - s0 : kBatchMaxSeg;
         B.in_mask = in_mask;
         B.out_mask = out_mask;
-        int vec_ok = n_per_seg % Vec16<T>::N == 0 ? 1 : 0;
+        int vec_ok = 1;  // tiles start at multiples of the vector length inside every segment: only the segment pointers must be 16-byte aligned
         for (int k = 0; k < Op::NIN; ++k) {
             B.s[k] = scalars ? scalars[k] : 0.0;
             for (int j = 0; j < B.n_seg; ++j) {
