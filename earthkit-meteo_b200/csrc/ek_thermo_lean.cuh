@@ -43,6 +43,9 @@
 #ifndef EK_LEAN_LOG_HILO
 #define EK_LEAN_LOG_HILO 1  // 1: k*ln2 added as a hi/lo pair (abs error of log_ ~2e-16); 0: one FMA less, ~1.5 ulp of the result
 #endif
+#ifndef EK_LEAN_REGROUP
+#define EK_LEAN_REGROUP 1  // 1: three regroupings that save one FP64 operation each (t_from_es, the Exner exponent, the "direct" fit)
+#endif
 #ifndef EK_LEAN_IMM
 #define EK_LEAN_IMM 1  // 1: the constants whose low 32 bits are zero (+-0.5, -0.25, the 1.5*2^52 rounding constant) are written as
                        // literals: they become 32-bit immediates of DFMA / DADD instead of occupying uniform registers, and a
@@ -60,8 +63,8 @@ struct Tables {
 // polynomial coefficients: constant bank -> uniform registers, never immediates
 __constant__ double kLog[5] = {-0.5, 0x1.5555555555555p-2 /*1/3*/, -0.25, 0x1.999999999999ap-3 /*1/5*/, -0x1.5555555555555p-3 /*-1/6*/};
 __constant__ double kExp[4] = {0.5, 0x1.5555555555555p-3 /*1/6*/, 0x1.5555555555555p-5 /*1/24*/, 0x1.1111111111111p-7 /*1/120*/};
-__constant__ double kRed[9] = {EK_INVLN2_N, EK_LN2N_HI, EK_LN2N_LO, EK_LN2_HI,   EK_LN2_LO, 0x1.8p52 /*magic*/,
-                               EK_LOG_P0,   EK_LOG_T0DJ, 0x1.62e42fefa39efp-1 /*ln 2*/};
+__constant__ double kRed[10] = {EK_INVLN2_N, EK_LN2N_HI, EK_LN2N_LO, EK_LN2_HI,   EK_LN2_LO, 0x1.8p52 /*magic*/,
+                                EK_LOG_P0,   EK_LOG_T0DJ, 0x1.62e42fefa39efp-1 /*ln 2*/, 0.285691 * EK_LOG_P0 /*kappa ln p0*/};
 
 __device__ __forceinline__ Tables* tables() {
     extern __shared__ __align__(16) unsigned char ek_smem_raw[];
@@ -192,7 +195,11 @@ __device__ __forceinline__ double log_p0_over(double x);
 __device__ __forceinline__ float log_p0_over(float x) { return (float)EK_LOG_P0 - __logf(x); }
 
 // kappa * ln(p0 / x): the exponent of the Exner factor, for callers that fold it into a larger exponential
+#if EK_LEAN_REGROUP
+__device__ __forceinline__ double kappa_log_p0_over(double x) { return fma(-::ek::kCdev.kappa, log_(x), kRed[9]); }  // kRed[9] = kappa ln p0
+#else
 __device__ __forceinline__ double kappa_log_p0_over(double x) { return ::ek::kCdev.kappa * (kRed[6] - log_(x)); }
+#endif
 __device__ __forceinline__ float kappa_log_p0_over(float x) { return (float)::ek::kC.kappa * ((float)EK_LOG_P0 - __logf(x)); }
 
 __device__ __forceinline__ double log_p0_over(double x) { return kRed[6] - log_(x); }

@@ -57,6 +57,8 @@ struct Consts {
     double b35_K3, neg_lam_b35_K0;               // T:1202-1203
     double b39_K1, b39_K2, b39_K4, b39_2K2, neg_b39_K1, neg_lam_b39_K0, neg_lam_b39_K1;  // T:1263-1266
     double wa0, wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4, inv_t0;  // wbpt "direct" rational fit (T:1051-1052)
+    double wsa1, wsa2, wsa3, wsa4, wsb1, wsb2, wsb3, wsb4;       // the same coefficients divided by 273.16^k (lean build: Horner in ept itself)
+    double td_K;                                                 // C3W (C4W - T0): t_from_es as C4W + td_K / (v - C3W) (lean build)
     double k10, k11, k12, k20, k21, k22, dD1, dD0, c121, c266, c058, c04;  // Davies-Jones first guess (T:1090-1128)
     double t_start, eps_default, neg_lambda, hundred, hundredth, c800, inv_800;
     double bis_c_ifs, bis_tie, bis_plim_scale;  // lean bisection (ek_thermo_formulas.inc: t_on_ma_bisect_tab_n)
@@ -126,6 +128,18 @@ constexpr Consts make_consts() {
     k.wb3 = -0.6899655;
     k.wb4 = -0.5929340;
     k.inv_t0 = 1.0 / 273.16;
+    {
+        constexpr double t1 = 273.16, t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2;
+        k.wsa1 = -20.68208 / t1;
+        k.wsa2 = 16.11182 / t2;
+        k.wsa3 = 2.574631 / t3;
+        k.wsa4 = -5.205688 / t4;
+        k.wsb1 = -3.552497 / t1;
+        k.wsb2 = 3.781782 / t2;
+        k.wsb3 = -0.6899655 / t3;
+        k.wsb4 = -0.5929340 / t4;
+    }
+    k.td_K = cdef::C3W * (cdef::C4W - cdef::T0);
     k.k10 = -53.737;
     k.k11 = 137.81;
     k.k12 = -38.5;
