@@ -262,11 +262,13 @@ __device__ __forceinline__ double atan2_(double y, double x) {
     const bool swap = ay > ax;
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
     const double z = mn * rcp_(mx);  // in [0, 1]
-    const bool m1 = z >= 0.4375, m2 = z >= 0.6875;
-    const double num = m2 ? z - 1.0 : (m1 ? fma(2.0, z, -1.0) : z);
-    const double den = m2 ? z + 1.0 : (m1 ? 2.0 + z : 1.0);
+    // z >= 7/16: atan(z) = pi/4 + atan((z - 1) / (z + 1)), |w| <= 0.392 on [7/16, 1]: inside the range of fdlibm's polynomial
+    // (|w| < 7/16), so its second break point (11/16, with atan(1/2)) is not needed on [0, 1]
+    const bool m = z >= 0.4375;
+    const double num = m ? z - 1.0 : z;
+    const double den = m ? z + 1.0 : 1.0;
     const double w = num * rcp_(den);
-    const double hi = m2 ? kTrig[18] : (m1 ? kTrig[16] : 0.0), lo = m2 ? kTrig[19] : (m1 ? kTrig[17] : 0.0);
+    const double hi = m ? kTrig[18] : 0.0, lo = m ? kTrig[19] : 0.0;
     const double w2 = w * w, w4 = w2 * w2;
     double s1 = fma(w4, kAtan[10], kAtan[8]);
     s1 = fma(w4, s1, kAtan[6]);
