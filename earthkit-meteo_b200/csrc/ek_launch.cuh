@@ -9,6 +9,10 @@
 
 #define EK_EXPORT __attribute__((visibility("default")))
 
+#ifndef EK_SMALL_WAVE_SPARE
+#define EK_SMALL_WAVE_SPARE 0  // CTA slots per SM a small-field launch leaves free for its successor in the stream (EK_PDL)
+#endif
+
 namespace ek {
 
 // defined in ek_api.cu
@@ -47,6 +51,25 @@ template <auto Kernel, typename... Args> inline void launch_kernel_smem(int bloc
 }
 template <auto Kernel, typename T, typename... Args> inline void launch_kernel(int blocks, cudaStream_t st, Args... args) {
     launch_kernel_smem<Kernel>(blocks, st, smem_for<T>(), args...);
+}
+
+// Launch of a streaming kernel that orders itself behind its predecessor in the stream with pdl_acquire() (ek_thermo_kernels.cuh):
+// the programmatic-serialization attribute lets it be scheduled while the predecessor drains.  ONLY for kernels that call
+// pdl_acquire() before their first access to a field -- without it the attribute would remove the stream dependency.
+template <auto Kernel, typename... Args>
+inline void launch_streaming(unsigned blocks, unsigned smem, cudaStream_t st, Args... args) {
+    prepare_smem<Kernel>(smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = EK_PDL ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, Kernel, args...);
 }
 
 // Launch Op over n points.  ins[k].ptr == NULL means broadcast scalar ins[k].value; outs[o] == NULL means
@@ -91,14 +114,13 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
     // small fields (a few tiles per resident CTA, e.g. one ERA5 level): exactly one resident wave -- every CTA copies the lean
     // tables once and walks its 2-3 tiles back to back instead of a second, partial wave of CTAs queueing behind the first
     // (theta + rh on 1 M points, graph replay: 14.4 -> 12.3 us; profiles/r02_kbench_era5_ctas.log)
-    const int64_t wave = (int64_t)sms * MinCtasOf<Op>::value;
+    const int64_t wave = (int64_t)sms * (MinCtasOf<Op>::value - EK_SMALL_WAVE_SPARE);
     if (ntiles <= 8 * wave && wave < cap) cap = wave;
     int64_t blocks = ntiles > tail_blocks ? ntiles : tail_blocks;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
 
-    prepare_smem<&ew_kernel<Op, OpE, T, unroll>>(smem_for<T>());
-    ew_kernel<Op, OpE, T, unroll><<<(unsigned)blocks, threads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(in, out, n, P, vec_ok);
+    launch_streaming<&ew_kernel<Op, OpE, T, unroll>>((unsigned)blocks, smem_for<T>(), static_cast<cudaStream_t>(stream), in, out, n, P, vec_ok);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
@@ -158,8 +180,7 @@ int launch_batch(const char* what, int n_seg, const void* const* const* ins, con
         int64_t blocks = ntiles > tail_blocks ? ntiles : tail_blocks;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        prepare_smem<&ew_batch_kernel<Op, OpE, T, unroll>>(smem_for<T>());
-        ew_batch_kernel<Op, OpE, T, unroll><<<(unsigned)blocks, kThreads, smem_for<T>(), static_cast<cudaStream_t>(stream)>>>(B, n_per_seg, P, vec_ok);
+        launch_streaming<&ew_batch_kernel<Op, OpE, T, unroll>>((unsigned)blocks, smem_for<T>(), static_cast<cudaStream_t>(stream), B, n_per_seg, P, vec_ok);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return set_error((int)err, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));

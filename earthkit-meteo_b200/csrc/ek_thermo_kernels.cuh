@@ -42,6 +42,12 @@
                              // (profiles/r02_ab_ew.log: suite 0.886 -> 0.923, ept + wet bulb 0.80 -> 0.86, single pass 0.76 -> 0.84);
                              // the short single-output kernels lose 7-10 % with it (theta 0.974 -> 0.871) and keep EK_MIN_CTAS
 #endif
+#ifndef EK_PDL
+#define EK_PDL 1  // programmatic dependent launch: a streaming kernel lets its successor in the stream start (launch latency, CTA
+                  // scheduling, the copy of the lean tables) while its own last CTAs drain; the successor waits for the
+                  // predecessor's completion and memory flush before it touches a field (griddepcontrol.wait).  One launch per
+                  // 1 M-point level, theta + rh: eager 13.3 -> 11.3 us, graph replay 11.8 -> 11.0 us (profiles/r02f_kbench_levels.log)
+#endif
 #ifndef EK_MIN_CTAS
 #define EK_MIN_CTAS 4  // <= 64 registers per thread: 4 CTAs = 32 warps per SM hide the fp64 dependency chains
 #endif
@@ -437,16 +443,33 @@ __device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutAr
 #endif
 }
 
+// Programmatic dependent launch (sm_90+).  pdl_release: the next kernel of the stream may be scheduled as soon as every CTA of
+// this grid has started; pdl_acquire: wait until the previous kernel of the stream has completed and its writes are visible.
+// Everything that reads or writes a field comes after pdl_acquire; only the table copy (immutable data) runs before it.
+// Both are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_release() {
+#if EK_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+__device__ __forceinline__ void pdl_acquire() {
+#if EK_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 template <class Op, class OpE, typename T, int UNROLL>
 __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
     ew_kernel(const InArgs<Op::NIN> in, const OutArgs<Op::NOUT> out, const int64_t n, const Params P, const int vec_ok) {
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;
     constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
+    pdl_release();
 #if EK_LEAN_DEVICE
     static_assert(sizeof(lean::Tables) == kSmemBytes, "kSmemBytes must match lean::Tables");
     if (sizeof(T) == 8) lean::init_tables();
 #endif
+    pdl_acquire();
     const int64_t ntiles = n / TILE;
     uint32_t array_mask = 0;
 #pragma unroll
@@ -493,9 +516,11 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
     constexpr int NIN = Op::NIN;
     constexpr int NOUT = Op::NOUT;
     constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
+    pdl_release();
 #if EK_LEAN_DEVICE
     if (sizeof(T) == 8) lean::init_tables();
 #endif
+    pdl_acquire();
     const int64_t tiles_per_seg = n_per_seg / TILE;
     const int64_t ntiles = tiles_per_seg * B.n_seg;
     const int64_t toff = (int64_t)threadIdx.x * Vec16<T>::N;

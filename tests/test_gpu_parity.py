@@ -482,6 +482,62 @@ def test_batched_suite_equals_per_field_launches(ek, dtype):
         fused.suite_tqp_batch(ts, qs[:-1], ps)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("n", [4099, 1_038_240, 6_599_680], ids=["tiny", "era5-level", "o1280-level"])
+def test_back_to_back_launches_keep_stream_order(ek, dtype, n):
+    """The streaming kernels are launched with programmatic stream serialization: a kernel may be scheduled while its
+    predecessor in the stream drains, and orders itself with griddepcontrol.wait before it touches a field.  A chain of launches
+    where each reads what the previous one wrote (RAW), overwrites what the previous one read (WAR) and rewrites its output
+    (WAW) must give the bits of the same chain run with a device synchronisation between the launches; a torch kernel in
+    the middle of the chain (launched without the attribute) and a CUDA-graph replay of the chain must too."""
+    from ek_thermo import fused, thermo
+
+    inp = random_inputs(n, seed=77)
+    t0, q, p = (torch.from_numpy(inp[k]).to(DEV).to(dtype) for k in ("t", "q", "p"))
+
+    def chain(sync, bufs):
+        a, b = bufs
+        a.copy_(t0)
+        for i in range(12):
+            # theta(a) -> b, then t_from_theta(b) back into a (a is read by the first launch and written by the second)
+            fused.suite_tqp(a, q, p, outputs=("theta",), out={"theta": b})
+            if sync:
+                torch.cuda.synchronize()
+            if i == 5:
+                b.mul_(1.0)  # an ordinary kernel in the chain
+            r = thermo.temperature_from_potential_temperature(b, p)
+            if sync:
+                torch.cuda.synchronize()
+            if i % 3 == 0:
+                a.copy_(r)
+            else:
+                fused.suite_tqp(r, q, p, outputs=("tv",), out={"tv": a})
+            if sync:
+                torch.cuda.synchronize()
+        return a.clone()
+
+    def same(x, y):
+        return bool(((x == y) | (torch.isnan(x) & torch.isnan(y))).all())
+
+    want = chain(True, (torch.empty_like(t0), torch.empty_like(t0)))
+    for _ in range(3):
+        assert same(chain(False, (torch.empty_like(t0), torch.empty_like(t0))), want)
+    # the same chain captured once and replayed (programmatic edges inside a graph)
+    bufs = (torch.empty_like(t0), torch.empty_like(t0))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        chain(False, bufs)  # warm-up on the capture stream (allocator, per-kernel attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        res = chain(False, bufs)
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        assert same(res, want)
+
+
 def test_sharded_run_equals_single_run(ek):
     """The partitioner's shards, run one by one on this GPU, reproduce the unsharded result exactly."""
     from ek_thermo import fused, partition
