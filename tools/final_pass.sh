@@ -7,9 +7,11 @@ mkdir -p $O
 python bench.py --impl reference > $O/r02f_bench_reference.json 2> $O/r02f_bench_reference.err
 python bench.py > $O/r02f_bench_default.json 2> $O/r02f_bench_default.err; echo "bench rc=$?"
 : > $O/r02f_bench_workloads.jsonl
-for w in suite_tqp_o1280x137_f64 suite_tqp_o1280x137_f32 suite_ttdp_o1280x137_f64 single_pass_tqp_o1280x137_f64 suite7_tqp_o1280x137_f64 suite7_tqp_o1280x137_f32 suite7_ttdp_o1280x137_f64 ept_wbpt_o1280x137_f64 ept_wbpt_o1280x137_f32 suite_tq_hybrid_o1280x137_f64 conv_ens_o640_shard_f64 theta_rh_era5_f64; do
+for w in suite_tqp_o1280x137_f64 suite_tqp_o1280x137_f32 suite_ttdp_o1280x137_f64 single_pass_tqp_o1280x137_f64 suite7_tqp_o1280x137_f64 suite7_tqp_o1280x137_f32 suite7_ttdp_o1280x137_f64 ept_wbpt_o1280x137_f64 ept_wbpt_o1280x137_f32 suite_tq_hybrid_o1280x137_f64 conv_ens_o640_shard_f64; do
   python bench.py --workload $w --steps 20 --warmup 5 --no-cpu 2> $O/r02f_bench_$w.err | tail -1 >> $O/r02f_bench_workloads.jsonl
 done
+# one ERA5 level is a 13 us step: enough steps for a steady state
+python bench.py --workload theta_rh_era5_f64 --steps 2000 --warmup 200 --no-cpu 2> $O/r02f_bench_theta_rh_era5_f64.err | tail -1 >> $O/r02f_bench_workloads.jsonl
 python - <<PY
 import json
 for ln in open("$O/r02f_bench_workloads.jsonl"):
@@ -23,6 +25,7 @@ python tools/kbench_hybrid.py > $O/r02f_kbench_hybrid.log 2>&1
 python tools/kbench_hybrid.py --f32 >> $O/r02f_kbench_hybrid.log 2>&1
 python tools/kbench_wind.py > $O/r02f_kbench_wind.log 2>&1
 python tools/kbench_wind.py --f32 >> $O/r02f_kbench_wind.log 2>&1
+python tools/kbench_scalar_p.py > $O/r02f_kbench_scalar_p.log 2>&1
 python tools/kbench_levels.py > $O/r02f_kbench_levels.log 2>&1
 python tools/kbench_levels.py --f32 >> $O/r02f_kbench_levels.log 2>&1
 python tools/hostbench.py --points 105594880 > $O/r02f_hostbench.log 2>&1
@@ -42,5 +45,9 @@ tools/ncu_capture.sh wbpt_newton_f64 ew_kernel 3 python tools/kbench.py --realis
 tools/ncu_capture.sh wbpt_bisect_f64 ew_kernel 3 python tools/kbench.py --realistic --only wbpt_bisect --iters 2 | head -12
 tools/ncu_capture.sh es_mixed_f64 ew_kernel 3 python tools/kbench.py --realistic --only es_mixed --iters 2 | head -12
 tools/ncu_capture.sh thickness_f64 column_geopotential_kernel 2 python tools/kbench_hybrid.py | head -12
+tools/ncu_capture.sh geometric_height_f64 column_geopotential_kernel 9 python tools/kbench_hybrid.py | head -12
 tools/ncu_capture.sh wind_speed_f64 ew_kernel 3 python tools/kbench_wind.py | head -12
+tools/ncu_capture.sh wind_direction_f64 ew_kernel 16 python tools/kbench_wind.py | head -12
+tools/ncu_capture.sh ept_wbpt_f32 ew_kernel 3 python bench.py --workload ept_wbpt_o1280x137_f32 $B | head -12
+tools/ncu_capture.sh suite7_ttdp_f64 ew_kernel 3 python bench.py --workload suite7_ttdp_o1280x137_f64 $B | head -12
 tail -3 $O/r02f_kbench_f64.log
