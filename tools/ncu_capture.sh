@@ -25,10 +25,13 @@ if len(rows) >= 3:
             "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__grid_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
-    print("== ${tag}")
-    for k in keys:
-        if k in d:
-            print(f"  {k:90s} {d[k]:>20s} {u[k]}")
+    try:
+        print("== ${tag}")
+        for k in keys:
+            if k in d:
+                print(f"  {k:90s} {d[k]:>20s} {u[k]}")
+    except BrokenPipeError:  # `| head`
+        pass
 else:
     print("== ${tag}: no kernel captured; see ${rep}.log")
 PY
