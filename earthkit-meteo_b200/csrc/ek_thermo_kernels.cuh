@@ -42,6 +42,9 @@
                              // (profiles/r02_ab_ew.log: suite 0.886 -> 0.923, ept + wet bulb 0.80 -> 0.86, single pass 0.76 -> 0.84);
                              // the short single-output kernels lose 7-10 % with it (theta 0.974 -> 0.871) and keep EK_MIN_CTAS
 #endif
+#ifndef EK_LAST_SCALAR_LOOP
+#define EK_LAST_SCALAR_LOOP 1  // a tile loop specialised for "every input an array, the last one a scalar" (pressure-level data)
+#endif
 #ifndef EK_PDL
 #define EK_PDL 1  // programmatic dependent launch: a streaming kernel lets its successor in the stream start (launch latency, CTA
                   // scheduling, the copy of the lean tables) while its own last CTAs drain; the successor waits for the
@@ -211,6 +214,14 @@ template <class Op> struct UnrollOf<Op, decltype((void)Op::UNROLL)> {
     static constexpr int value = Op::UNROLL > 0 ? Op::UNROLL : EK_UNROLL;
 };
 
+// The "last input is a scalar" tile loop (load_tile ALLARR == 2) unless the functor opts out with LAST_SCALAR_LOOP = false
+template <class Op, class = void> struct LastScalarLoopOf {
+    static constexpr bool value = EK_LAST_SCALAR_LOOP != 0;
+};
+template <class Op> struct LastScalarLoopOf<Op, decltype((void)Op::LAST_SCALAR_LOOP)> {
+    static constexpr bool value = EK_LAST_SCALAR_LOOP != 0 && Op::LAST_SCALAR_LOOP;
+};
+
 template <class Op, class = void> struct DeferColdOf {
     static constexpr bool value = false;
 };
@@ -231,15 +242,21 @@ template <class Op, typename T, int UNROLL> struct TileRegs {
     T x[Op::NIN][UNROLL][Vec16<T>::N];
 };
 
-// ALLARR: every input is an array (the whole-field call): no broadcast value is materialised in the tile's registers and the
-// loads carry no predicate (measured in the SASS of the ept kernel: 6 of 160 instructions per point were those moves)
-template <class Op, typename T, int UNROLL, bool VECOK, bool ALLARR>
+// ALLARR (the shape of the call, fixed at compile time so the loop carries no predicated loads and no broadcast moves):
+//   1  every input is an array (the whole-field call; measured in the SASS of the ept kernel: 6 of 160 instructions per
+//      point were those moves);
+//   2  every input but the LAST is an array and the last is a broadcast scalar -- pressure-level data (t, q arrays; p one
+//      number): the scalar is a loop invariant the compiler can see, so everything that depends on p alone (ln(p0/p), the Exner
+//      factor) is computed once per thread instead of once per point;
+//   0  anything else (run-time mask).
+template <class Op, typename T, int UNROLL, bool VECOK, int ALLARR>
 __device__ __forceinline__ void load_tile(TileRegs<Op, T, UNROLL>& r, const InArgs<Op::NIN>& in, const int64_t base) {
     constexpr int VEC = Vec16<T>::N;
     constexpr int VSTRIDE = kThreads * VEC;  // elements between a thread's successive vectors
 #pragma unroll
     for (int k = 0; k < Op::NIN; ++k) {
-        if (ALLARR || in.p[k] != nullptr) {
+        const bool is_array = ALLARR == 1 ? true : (ALLARR == 2 ? k < Op::NIN - 1 : in.p[k] != nullptr);
+        if (is_array) {
             const T* src = static_cast<const T*>(in.p[k]) + base;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -410,7 +427,7 @@ __device__ __forceinline__ void compute_store_tile(const TileRegs<Op, T, UNROLL>
 // Tiles are handed to CTAs round-robin.  The loop is software-pipelined in registers: the loads of a CTA's NEXT
 // tile are issued before the math of the current one, so every warp keeps HBM requests in flight while it
 // computes (two register sets, A and B, alternate; no dynamic register indexing).
-template <class Op, class OpE, typename T, int UNROLL, bool VECOK, bool ALLARR>
+template <class Op, class OpE, typename T, int UNROLL, bool VECOK, int ALLARR>
 __device__ __forceinline__ void tile_loop(const InArgs<Op::NIN>& in, const OutArgs<Op::NOUT>& out, const int64_t ntiles, const Params& P,
                                           const uint32_t array_mask) {
     constexpr int TILE = kThreads * Vec16<T>::N * UNROLL;
@@ -475,11 +492,13 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
 #pragma unroll
     for (int k = 0; k < NIN; ++k) array_mask |= (in.p[k] != nullptr) ? (1u << k) : 0u;
     if (vec_ok && array_mask == (1u << NIN) - 1u)
-        tile_loop<Op, OpE, T, UNROLL, true, true>(in, out, ntiles, P, array_mask);
+        tile_loop<Op, OpE, T, UNROLL, true, 1>(in, out, ntiles, P, array_mask);
+    else if (LastScalarLoopOf<Op>::value && NIN >= 2 && vec_ok && array_mask == (1u << (NIN - 1)) - 1u)
+        tile_loop<Op, OpE, T, UNROLL, true, 2>(in, out, ntiles, P, array_mask);
     else if (vec_ok)
-        tile_loop<Op, OpE, T, UNROLL, true, false>(in, out, ntiles, P, array_mask);
+        tile_loop<Op, OpE, T, UNROLL, true, 0>(in, out, ntiles, P, array_mask);
     else
-        tile_loop<Op, OpE, T, UNROLL, false, false>(in, out, ntiles, P, array_mask);
+        tile_loop<Op, OpE, T, UNROLL, false, 0>(in, out, ntiles, P, array_mask);
 
     // tail: fewer than one tile of points, one point per thread, grid-stride
     for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
@@ -539,11 +558,11 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
         for (int o = 0; o < NOUT; ++o) out.p[o] = ((B.out_mask >> o) & 1u) ? B.out[o][seg] : nullptr;
         TileRegs<Op, T, UNROLL> A;
         if (vec_ok && all_arrays)
-            load_tile<Op, T, UNROLL, true, true>(A, in, base);
+            load_tile<Op, T, UNROLL, true, 1>(A, in, base);
         else if (vec_ok)
-            load_tile<Op, T, UNROLL, true, false>(A, in, base);
+            load_tile<Op, T, UNROLL, true, 0>(A, in, base);
         else
-            load_tile<Op, T, UNROLL, false, false>(A, in, base);
+            load_tile<Op, T, UNROLL, false, 0>(A, in, base);
         if (Op::PREFETCH_NEXT) {  // the CTA's tile EK_PF_DIST rounds ahead, possibly in a later segment
             const int64_t nt = tile + EK_PF_DIST * (int64_t)gridDim.x;
             if (nt < ntiles) {

@@ -815,6 +815,62 @@ def test_host_array_front_end_numpy_semantics(ek):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_pressure_level_calls_equal_array_calls(ek, dtype):
+    """Pressure-level data: t (and q / td) arrays, p ONE number.  The kernels run a tile loop specialised for that shape, in
+    which everything that depends on p alone is computed once per thread; the results must be the bits of the same call
+    with p materialised as a constant array -- single functions, suites (every ept formulation), the two-output ept kernel,
+    the iterative solvers, ragged and unaligned fields, special values in t and a pressure that makes the NaN rule fire."""
+    from ek_thermo import fused, thermo
+
+    inp = random_inputs(N_RANDOM + 1, seed=91)
+    t, q, td, ept = (torch.from_numpy(inp[k]).to(DEV).to(dtype) for k in ("t", "q", "td", "ept"))
+    t[::1001] = float("nan")
+    t[5::1777] = float("inf")
+    t[7::1999] = 0.0
+
+    def same(a, b, what):
+        assert a.shape == b.shape and bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all()), what
+
+    # every function of the case table that takes two or more fields: its last field as one number
+    np_dtype = np.float64 if dtype == torch.float64 else np.float32
+    for case in CASES:
+        if len(case.args) < 2:
+            continue
+        arrs = [torch.from_numpy(inp[a].astype(np_dtype)).to(DEV) for a in case.args[:-1]]
+        arrs[0][::1001] = float("nan")
+        arrs[0][3::1013] = 0.0
+        fn = getattr(thermo, case.fn)
+        for s0 in (float(np.median(inp[case.args[-1]])), 3.0):
+            got = fn(*arrs, s0, **case.kwargs)
+            want = fn(*arrs, torch.full_like(arrs[0], s0), **case.kwargs)
+            for k, (g, w) in enumerate(zip(got if isinstance(got, tuple) else (got,), want if isinstance(want, tuple) else (want,))):
+                same(g, w, (case.id, s0, k))
+
+    for off in (0, 1):  # 16-byte aligned fields, and views that start one element later (the scalar load/store path)
+        tt, qq, dd, ee = t[off:], q[off:], td[off:], ept[off:]
+        for p0 in (85000.0, 1.0e5, 3.0, 20000.0):  # 3 Pa: p - es < 1e-4 on most points (T:194)
+            pa = torch.full_like(tt, p0)
+            same(thermo.potential_temperature(tt, p0), thermo.potential_temperature(tt, pa), ("theta", p0, off))
+            same(thermo.relative_humidity_from_specific_humidity(tt, qq, p0), thermo.relative_humidity_from_specific_humidity(tt, qq, pa), ("rh", p0, off))
+            same(thermo.dewpoint_from_specific_humidity(qq, p0), thermo.dewpoint_from_specific_humidity(qq, pa), ("td", p0, off))
+            same(thermo.saturation_specific_humidity(tt, p0), thermo.saturation_specific_humidity(tt, pa), ("qs", p0, off))
+            same(thermo.ept_from_specific_humidity(tt, qq, p0), thermo.ept_from_specific_humidity(tt, qq, pa), ("ept", p0, off))
+            same(thermo.ept_from_dewpoint(tt, dd, p0, method="bolton39"), thermo.ept_from_dewpoint(tt, dd, pa, method="bolton39"), ("ept39", p0, off))
+            for tm in ("bisect", "newton"):
+                same(thermo.temperature_on_moist_adiabat(ee, p0, t_method=tm), thermo.temperature_on_moist_adiabat(ee, pa, t_method=tm), (tm, p0, off))
+            for em in ("ifs", "bolton35", "bolton39"):
+                for outputs in (fused.DEFAULT_TQP, ("theta", "rh"), fused.ALL7_TQP, tuple(fused.SUITE_TQP_OUTPUTS)):
+                    a, b = fused.suite_tqp(tt, qq, p0, outputs=outputs, ept_method=em), fused.suite_tqp(tt, qq, pa, outputs=outputs, ept_method=em)
+                    for name in outputs:
+                        same(a[name], b[name], ("suite_tqp", em, name, p0, off))
+                a, b = fused.suite_ttdp(tt, dd, p0, outputs=fused.ALL7_TTDP, ept_method=em), fused.suite_ttdp(tt, dd, pa, outputs=fused.ALL7_TTDP, ept_method=em)
+                for name in fused.ALL7_TTDP:
+                    same(a[name], b[name], ("suite_ttdp", em, name, p0, off))
+                for x, y in zip(fused.ept_wet_bulb(tt, qq, p0, humidity="q", ept_method=em), fused.ept_wet_bulb(tt, qq, pa, humidity="q", ept_method=em)):
+                    same(x, y, ("ept_wet_bulb", em, p0, off))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
 def test_fused_results_do_not_depend_on_position(ek, dtype):
     """A point's result is the same bits whether it is computed in the vector body of a tile or in the scalar tail, in a
     whole-field launch or in a launch over a piece of the field: the fused suites and the ept / wet-bulb kernel on
