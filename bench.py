@@ -635,7 +635,8 @@ def run_e2e(args, wl, arrays, hyb, out, n_slabs, device, world, barrier, max_ove
 
     el = timed(call)
     e2e = {"value": world * steps * n_e2e / el, "unit": "grid-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(outputs) * esz * n_e2e,
-           "steps": steps, "step_seconds_rank0": list(per_step), "pcie_gbs_all_gpus": world * (h2d + len(outputs) * esz * n_e2e) * steps / el / 1e9,
+           "steps": steps, "step_seconds_rank0": list(per_step), "value_median_step_rank0": n_e2e / float(np.median(per_step)),
+           "pcie_gbs_all_gpus": world * (h2d + len(outputs) * esz * n_e2e) * steps / el / 1e9,
            "sample": f"{lv} of {n_slabs} level slabs per step ({n_e2e} points) through ek_thermo.hostpipe.HostSuite, page-locked host buffers"}
     # the device result of the timed steps and the host-pipeline result agree bit for bit on the shared slab
     name0 = outputs[0]
@@ -653,6 +654,8 @@ def run_e2e(args, wl, arrays, hyb, out, n_slabs, device, world, barrier, max_ove
         assert np.array_equal(res[name0][:100000], dev_res, equal_nan=True), "host.fused and device path differ"
         e2e_pageable = {"value": world * steps * n_e2e / el, "unit": "grid-points/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": len(outputs) * esz * n_e2e, "steps": steps, "step_seconds_rank0": list(per_step),
+                        # the staging threads share the VM's cores: single steps of 3-8 x the median turn up on busy hosts
+                        "value_median_step_rank0": n_e2e / float(np.median(per_step)),
                         "sample": f"{n_e2e} points per step through ek_thermo.host.fused: pageable numpy arrays in (staged by worker threads), "
                                   "fresh page-locked result arrays out (torch's caching host allocator; first call excluded as warm-up)"}
         host.release_staging()
