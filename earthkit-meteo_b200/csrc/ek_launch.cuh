@@ -129,10 +129,11 @@ int launch(const char* what, const ek_operand* ins, void* const* outs, int64_t n
 
 // Op over n_seg separate fields of n_per_seg points each in one launch (ew_batch_kernel).  ins[k]: host array of n_seg device
 // pointers, or NULL for the broadcast scalar scalars[k]; outs[o]: host array of n_seg device pointers, or NULL when output o
-// is not wanted.  More than kBatchMaxSeg segments take one launch per kBatchMaxSeg.
+// is not wanted.  last_scalars: NULL, or n_seg numbers -- the LAST input as one broadcast scalar per segment (then ins[NIN-1] must
+// be NULL).  More than kBatchMaxSeg segments take one launch per kBatchMaxSeg.
 template <class Op, class OpE, typename T>
-int launch_batch(const char* what, int n_seg, const void* const* const* ins, const double* scalars, void* const* const* outs, int64_t n_per_seg,
-                 Params P, void* stream) {
+int launch_batch(const char* what, int n_seg, const void* const* const* ins, const double* scalars, const double* last_scalars,
+                 void* const* const* outs, int64_t n_per_seg, Params P, void* stream) {
     if (n_seg < 0 || n_per_seg < 0) return set_error(EK_ERR_ARG, "%s: n_seg=%d n_per_seg=%lld", what, n_seg, (long long)n_per_seg);
     uint32_t in_mask = 0, out_mask = 0;
     for (int k = 0; k < Op::NIN; ++k)
@@ -140,6 +141,7 @@ int launch_batch(const char* what, int n_seg, const void* const* const* ins, con
     for (int o = 0; o < Op::NOUT; ++o)
         if (outs[o]) out_mask |= 1u << o;
     if (out_mask == 0) return set_error(EK_ERR_ARG, "%s: no output buffer given", what);
+    if (last_scalars && ins[Op::NIN - 1]) return set_error(EK_ERR_ARG, "%s: the last input is given both as fields and as per-segment scalars", what);
     P.out_mask = out_mask;
     if (n_seg == 0 || n_per_seg == 0) return EK_OK;
     const int sms = sm_count_current_device();
@@ -151,6 +153,8 @@ int launch_batch(const char* what, int n_seg, const void* const* const* ins, con
         B.n_seg = n_seg - s0 < kBatchMaxSeg ? n_seg - s0 : kBatchMaxSeg;
         B.in_mask = in_mask;
         B.out_mask = out_mask;
+        B.last_per_seg = last_scalars ? 1 : 0;
+        for (int j = 0; j < B.n_seg; ++j) B.s_last[j] = last_scalars ? last_scalars[s0 + j] : 0.0;
         int vec_ok = 1;  // tiles start at multiples of the vector length inside every segment: only the segment pointers must be 16-byte aligned
         for (int k = 0; k < Op::NIN; ++k) {
             B.s[k] = scalars ? scalars[k] : 0.0;

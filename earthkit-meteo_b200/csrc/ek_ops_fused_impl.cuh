@@ -41,7 +41,7 @@ static int suite(const char* what, ek_operand a, ek_operand b, ek_operand c, voi
 // formulation, plus the compile-time sets a per-level caller is most likely to ask for.
 template <template <uint32_t, int> class OpM, template <uint32_t, int> class OpME, typename T>
 static int suite_batch(const char* what, int n_seg, const void* const* a, const void* const* b, const void* const* c, const double* scalars,
-                       void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream) {
+                       const double* level_scalars, void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream) {
     if (!outs) return set_error(EK_ERR_ARG, "%s: outs is NULL", what);
     if (out_mask == 0 || out_mask >= (1u << S_NSLOTS)) return set_error(EK_ERR_ARG, "%s: out_mask=0x%x selects no valid output", what, out_mask);
     void* const* o[S_NSLOTS];
@@ -55,13 +55,13 @@ static int suite_batch(const char* what, int n_seg, const void* const* a, const 
     switch (ept_method) {
         case EK_EPT_IFS:
             switch (out_mask) {
-                case 0x1F: return launch_batch<OpM<0x1F, EPT_IFS>, OpME<0x1F, EPT_IFS>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
-                case 0x05: return launch_batch<OpM<0x05, EPT_IFS>, OpME<0x05, EPT_IFS>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
-                case 0x31F: return launch_batch<OpM<0x31F, EPT_IFS>, OpME<0x31F, EPT_IFS>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
-                default: return launch_batch<OpM<0, EPT_IFS>, OpME<0, EPT_IFS>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
+                case 0x1F: return launch_batch<OpM<0x1F, EPT_IFS>, OpME<0x1F, EPT_IFS>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
+                case 0x05: return launch_batch<OpM<0x05, EPT_IFS>, OpME<0x05, EPT_IFS>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
+                case 0x31F: return launch_batch<OpM<0x31F, EPT_IFS>, OpME<0x31F, EPT_IFS>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
+                default: return launch_batch<OpM<0, EPT_IFS>, OpME<0, EPT_IFS>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
             }
-        case EK_EPT_BOLTON35: return launch_batch<OpM<0, EPT_BOLTON35>, OpME<0, EPT_BOLTON35>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
-        case EK_EPT_BOLTON39: return launch_batch<OpM<0, EPT_BOLTON39>, OpME<0, EPT_BOLTON39>, T>(what, n_seg, ins, scalars, o, n_per_seg, Params{}, stream);
+        case EK_EPT_BOLTON35: return launch_batch<OpM<0, EPT_BOLTON35>, OpME<0, EPT_BOLTON35>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
+        case EK_EPT_BOLTON39: return launch_batch<OpM<0, EPT_BOLTON39>, OpME<0, EPT_BOLTON39>, T>(what, n_seg, ins, scalars, level_scalars, o, n_per_seg, Params{}, stream);
     }
     return set_error(EK_ERR_ENUM, "%s: invalid ept method id %d", what, ept_method);
 }

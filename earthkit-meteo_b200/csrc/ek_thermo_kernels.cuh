@@ -524,6 +524,8 @@ template <int NIN, int NOUT> struct BatchArgs {
     const void* in[NIN][kBatchMaxSeg];
     void* out[NOUT][kBatchMaxSeg];
     double s[NIN];       // broadcast scalar of input k when in[k][0] == NULL (the same for every segment)
+    double s_last[kBatchMaxSeg];  // last_per_seg: the LAST input as one number per segment (pressure-level data: t, q fields; p per level)
+    int last_per_seg;
     uint32_t in_mask;    // bit k: input k is an array
     uint32_t out_mask;   // bit o: output o is written
     int n_seg;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
 #pragma unroll
         for (int k = 0; k < NIN; ++k) {
             in.p[k] = ((B.in_mask >> k) & 1u) ? B.in[k][seg] : nullptr;
-            in.s[k] = B.s[k];
+            in.s[k] = (k == NIN - 1 && B.last_per_seg) ? B.s_last[seg] : B.s[k];
         }
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) out.p[o] = ((B.out_mask >> o) & 1u) ? B.out[o][seg] : nullptr;
@@ -586,7 +588,9 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
         const int64_t i = tiles_per_seg * TILE + (j - (int64_t)seg * tail);
         T a[NIN], r[NOUT];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) a[k] = ((B.in_mask >> k) & 1u) ? __ldcs(static_cast<const T*>(B.in[k][seg]) + i) : static_cast<T>(B.s[k]);
+        for (int k = 0; k < NIN; ++k)
+            a[k] = ((B.in_mask >> k) & 1u) ? __ldcs(static_cast<const T*>(B.in[k][seg]) + i)
+                                           : static_cast<T>((k == NIN - 1 && B.last_per_seg) ? B.s_last[seg] : B.s[k]);
         point<Op, OpE, T>(a, r, P, B.in_mask);
 #pragma unroll
         for (int o = 0; o < NOUT; ++o)

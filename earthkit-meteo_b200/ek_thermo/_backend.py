@@ -107,7 +107,8 @@ for _name in ("suite_tqp", "suite_ttdp"):
 for _name in ("suite_tqp_batch", "suite_ttdp_batch"):
     for _sfx in ("f64", "f32"):
         _fn = getattr(_lib, f"ek_thermo_{_name}_{_sfx}")
-        _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_double), ctypes.POINTER(c_void_p), c_uint32, c_int, c_int64, c_void_p]
+        _fn.argtypes = [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_double), ctypes.POINTER(c_double), ctypes.POINTER(c_void_p), c_uint32, c_int,
+                        c_int64, c_void_p]
         _fn.restype = c_int
 _c_int_p = ctypes.POINTER(c_int)
 for _sfx in ("f64", "f32"):
@@ -367,12 +368,20 @@ def execute_suite(symbol: str, args, out_names, slots, out=None, ept_method=0):
 
 def execute_suite_batch(symbol: str, seg_args, out_names, slots, outs=None, ept_method=0):
     """Run a fused suite over a list of separate fields in one launch.  seg_args: three items, each a list of same-shape
-    contiguous CUDA tensors (one per field) or a Python number (broadcast).  Returns a list of {name: tensor}, one per field."""
+    contiguous CUDA tensors (one per field) or a Python number (broadcast); the LAST item may also be a list of Python numbers,
+    one per field (pressure-level data: one pressure per level).  Returns a list of {name: tensor}, one per field."""
+    def _numbers(a):
+        return isinstance(a, (list, tuple)) and len(a) > 0 and all(isinstance(v, (int, float)) and not isinstance(v, bool) for v in a)
+
+    level_scalars = None
+    if _numbers(seg_args[-1]):
+        level_scalars = [float(v) for v in seg_args[-1]]
+        seg_args = (*seg_args[:-1], 0.0)
     lists = [a for a in seg_args if isinstance(a, (list, tuple))]
     if not lists:
         raise TypeError("ek_thermo: a batched suite needs at least one list of CUDA tensors")
     n_seg = len(lists[0])
-    if any(len(a) != n_seg for a in lists):
+    if any(len(a) != n_seg for a in lists) or (level_scalars is not None and len(level_scalars) != n_seg):
         raise ValueError("ek_thermo: the input lists of a batched suite must have one length")
     res = [dict() for _ in range(n_seg)]
     if n_seg == 0:
@@ -421,7 +430,8 @@ def execute_suite_batch(symbol: str, seg_args, out_names, slots, outs=None, ept_
         mask |= 1 << k
     n = first.numel()
     if n > 0:
-        _call(symbol, dtype, dev, [n_seg, *ptr_arrays, scalars, out_tab, mask, ept_method, n])
+        lv = (c_double * n_seg)(*level_scalars) if level_scalars is not None else None
+        _call(symbol, dtype, dev, [n_seg, *ptr_arrays, scalars, lv, out_tab, mask, ept_method, n])
     del keep
     return res
 

@@ -75,9 +75,10 @@ def suite_ttdp(t, td, p, outputs=DEFAULT_TTDP, out=None, ept_method="ifs"):
 def suite_tqp_batch(ts, qs, ps, outputs=DEFAULT_TQP, out=None, ept_method="ifs"):
     """``suite_tqp`` over a LIST of separate fields (one tensor per level / member, each its own allocation) in one launch.
 
-    ``ts`` / ``qs`` / ``ps`` are lists of same-shape contiguous CUDA tensors, or a Python number for a broadcast operand (a
-    pressure level).  Returns ``[{name: tensor}, ...]``, one dict per field; every value is bit-identical to
-    ``suite_tqp(ts[j], qs[j], ps[j])``.  A launch per 1 M-point level is bound by launch and pipeline-fill latency
+    ``ts`` / ``qs`` / ``ps`` are lists of same-shape contiguous CUDA tensors, or a Python number for a broadcast operand; ``ps``
+    may also be a list of Python numbers, ONE PRESSURE PER FIELD -- pressure-level data, the reference user's loop
+    ``for lev: potential_temperature(t[lev], p_lev)`` in one launch.  Returns ``[{name: tensor}, ...]``, one dict per field; every
+    value is bit-identical to ``suite_tqp(ts[j], qs[j], ps[j])``.  A launch per 1 M-point level is bound by launch and pipeline-fill latency
     (12-16 us for 6 us of HBM time); one launch over all levels is not."""
     outputs = tuple(outputs)
     return _b.execute_suite_batch("suite_tqp_batch", (ts, qs, ps), outputs, _slots(SUITE_TQP_OUTPUTS, outputs), out, _ept_id(ept_method))

@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define EK_THERMO_VERSION 110 /* 0.1.1: suite slots 8 (ept) / 9 (wbpt) and their ept_method argument; host pipelines for every suite */
+#define EK_THERMO_VERSION 111 /* 0.1.1: suite slots 8 (ept) / 9 (wbpt) and their ept_method argument; host pipelines for every suite;
+                                  batched suites with one pressure per level */
 
 typedef struct ek_operand {
     const void* ptr; /* device pointer, or NULL for a broadcast scalar */
@@ -143,12 +144,14 @@ EK_THERMO_FN(suite_ttdp, ek_operand t, ek_operand td, ek_operand p, void* const*
 /* The suites over n_seg SEPARATE fields of n_per_seg points each (one allocation per level / member, as a per-level caller
  * holds them) in ONE launch: a launch per 1 M-point level is latency-bound (12-16 us for 6 us of HBM time).  t / h / p: HOST
  * arrays of n_seg DEVICE pointers, or NULL for the broadcast scalar scalars[k] (k = 0, 1, 2); outs[k]: HOST array of n_seg
- * DEVICE pointers for slot k, or NULL when bit k of out_mask is clear.  The pointer tables are copied into the kernel
- * parameters at launch; results are bit-identical to n_seg separate suite launches. */
+ * DEVICE pointers for slot k, or NULL when bit k of out_mask is clear.  level_scalars: NULL, or a HOST array of n_seg numbers --
+ * the pressure as ONE number per field (pressure-level data: the loop `for lev: theta(t[lev], p_lev)` of a reference user in one
+ * launch); p must then be NULL.  The pointer tables and level scalars are copied into the kernel parameters at launch; results
+ * are bit-identical to n_seg separate suite launches. */
 EK_THERMO_FN(suite_tqp_batch, int n_seg, const void* const* t, const void* const* q, const void* const* p, const double* scalars,
-             void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream)
+             const double* level_scalars, void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream)
 EK_THERMO_FN(suite_ttdp_batch, int n_seg, const void* const* t, const void* const* td, const void* const* p, const double* scalars,
-             void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream)
+             const double* level_scalars, void* const* const* outs, uint32_t out_mask, int ept_method, int64_t n_per_seg, void* stream)
 /* (t, h, p) -> ept and/or the wet-bulb (potential) temperature in one pass.  h is td or q (humidity_kind),
  * at_p0 = 1 gives the wet-bulb POTENTIAL temperature; either output pointer may be NULL (but not both);
  * t_method EK_TM_NONE computes ept only */

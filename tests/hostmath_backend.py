@@ -56,14 +56,17 @@ def fake_call(symbol, dtype, device, c_args):
     from ek_thermo import _backend as b
 
     if symbol in ("suite_tqp_batch", "suite_ttdp_batch"):  # one mock "launch" per field: the per-field operands are read back from the pointer tables
-        n_seg, pa, pb, pc, scalars, out_tab, mask, em, n = c_args
+        n_seg, pa, pb, pc, scalars, level_scalars, out_tab, mask, em, n = c_args
         mask = _val(mask)
         base = symbol[:-len("_batch")]
         for j in range(_val(n_seg)):
             ops = []
             for k, tab in enumerate((pa, pb, pc)):
                 tab = _val(tab)
-                ops.append(b.ek_operand(ctypes.cast(tab, ctypes.POINTER(c_void_p))[j], 0.0) if tab else b.ek_operand(None, scalars[k]))
+                if tab:
+                    ops.append(b.ek_operand(ctypes.cast(tab, ctypes.POINTER(c_void_p))[j], 0.0))
+                else:
+                    ops.append(b.ek_operand(None, level_scalars[j] if (k == 2 and level_scalars is not None) else scalars[k]))
             o = [ctypes.cast(out_tab[k], ctypes.POINTER(c_void_p))[j] if (mask >> k) & 1 else None for k in range(b.N_SUITE_SLOTS)]
             _run(base, dtype, ops, o, _val(n), mask=mask, m=_val(em))
         return None

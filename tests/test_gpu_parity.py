@@ -470,6 +470,22 @@ def test_batched_suite_equals_per_field_launches(ek, dtype):
         want = fused.suite_ttdp(ts[j], tds[j], 85000.0, outputs=fused.ALL7_TTDP)
         for name in fused.ALL7_TTDP:
             assert same(got[j][name], want[name]), (j, name)
+    # pressure-level data: one pressure PER FIELD (150 levels: two launches, the second one starts at level 128)
+    levels = [float(x) for x in np.linspace(100.0, 101325.0, n_seg)]
+    levels[3] = 3.0  # p - es < 1e-4 on most points: the NaN rule
+    for outputs, em in ((("theta", "rh"), "ifs"), (fused.ALL7_TQP, "ifs"), (fused.ALL7_TQP, "bolton39")):
+        got = fused.suite_tqp_batch(ts, qs, levels, outputs=outputs, ept_method=em)
+        for j in (0, 3, 64, 127, 128, n_seg - 1):
+            want = fused.suite_tqp(ts[j], qs[j], levels[j], outputs=outputs, ept_method=em)
+            for name in outputs:
+                assert same(got[j][name], want[name]), ("levels", outputs, em, j, name)
+    got = fused.suite_ttdp_batch(ts, tds, levels)
+    for j in (1, 128, n_seg - 1):
+        want = fused.suite_ttdp(ts[j], tds[j], levels[j])
+        for name in fused.DEFAULT_TTDP:
+            assert same(got[j][name], want[name]), ("levels ttdp", j, name)
+    with pytest.raises(ValueError):
+        fused.suite_tqp_batch(ts, qs, levels[:-1])
     # views at an odd element offset: not 16-byte aligned -> the scalar load/store path of the same kernel
     tv, qv, pv = (fields(k, off=1) for k in ("t", "q", "p"))
     got = fused.suite_tqp_batch(tv, qv, pv)

@@ -130,6 +130,15 @@ def test_batched_suite_host_logic(monkeypatch):
         assert got[j]["q"].data_ptr() == pre[j]["q"].data_ptr()
         want = fused.suite_ttdp(ts[j], tds[j], 85000.0, outputs=("q", "wbpt"))
         assert torch.equal(torch.nan_to_num(got[j]["wbpt"]), torch.nan_to_num(want["wbpt"]))
+    # pressure-level data: one pressure per field
+    levels = [100000.0, 85000.0, 50000, 3.0]
+    got = fused.suite_tqp_batch(ts, qs, levels, outputs=("theta", "rh", "td", "ept", "wbpt"))
+    for j in range(4):
+        want = fused.suite_tqp(ts[j], qs[j], float(levels[j]), outputs=("theta", "rh", "td", "ept", "wbpt"))
+        for name in want:
+            assert torch.equal(torch.nan_to_num(got[j][name]), torch.nan_to_num(want[name])), (j, name)
+    with pytest.raises(ValueError):
+        fused.suite_tqp_batch(ts, qs, levels[:3])
     assert fused.suite_tqp_batch([], [], []) == []
     with pytest.raises(ValueError):
         fused.suite_tqp_batch(ts, qs[:3], ps)

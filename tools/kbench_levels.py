@@ -90,3 +90,23 @@ print(f"theta + rh, {nlev} levels x {npl} points, {dtype}, {bpp} B/pt, roofline 
 for name, ms in rows:
     us = ms * 1e3 / nlev
     print(f"{name:42s} {us:7.2f} us per level  {npl / us / 1e3:7.1f} Gpt/s  frac={bpp * npl / us / 1e3 / peak:.3f}")
+
+# pressure-level data (ERA5 on pressure levels): t and q fields, the pressure ONE NUMBER per level -- 2 arrays in, 2 out
+plev = [float(p[0]) for p in ps]
+bpp_l = ts[0].element_size() * (2 + len(outputs))
+
+
+def per_level_scalar():
+    for k in range(nlev):
+        fused.suite_tqp(ts[k], qs[k], plev[k], outputs=outputs, out=outs[k])
+
+
+def batched_scalar():
+    fused.suite_tqp_batch(ts, qs, plev, outputs=outputs, out=outs)
+
+
+rows = [("one launch per level, eager", timed(per_level_scalar)), ("one batched launch, one pressure per level", timed(batched_scalar))]
+print(f"pressure levels: theta + rh, {nlev} levels x {npl} points, scalar p per level, {bpp_l} B/pt, roofline {bpp_l * npl / peak / 1e3:.2f} us per level")
+for name, ms in rows:
+    us = ms * 1e3 / nlev
+    print(f"{name:42s} {us:7.2f} us per level  {npl / us / 1e3:7.1f} Gpt/s  frac={bpp_l * npl / us / 1e3 / peak:.3f}")
