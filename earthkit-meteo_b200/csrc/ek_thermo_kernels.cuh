@@ -558,23 +558,36 @@ __global__ void __launch_bounds__(kThreads, MinCtasOf<Op>::value)
         }
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) out.p[o] = ((B.out_mask >> o) & 1u) ? B.out[o][seg] : nullptr;
+        auto prefetch_next = [&]() {
+            if (Op::PREFETCH_NEXT) {  // the CTA's tile EK_PF_DIST rounds ahead, possibly in a later segment
+                const int64_t nt = tile + EK_PF_DIST * (int64_t)gridDim.x;
+                if (nt < ntiles) {
+                    const int nseg = (int)(nt / tiles_per_seg);
+                    InArgs<NIN> nin;
+    #pragma unroll
+                    for (int k = 0; k < NIN; ++k) nin.p[k] = ((B.in_mask >> k) & 1u) ? B.in[k][nseg] : nullptr;
+                    prefetch_tile_l2<Op, T, UNROLL>(nin, (nt - (int64_t)nseg * tiles_per_seg) * TILE + toff);
+                }
+            }
+        };
         TileRegs<Op, T, UNROLL> A;
+        if constexpr (LastScalarLoopOf<Op>::value && NIN >= 2) {
+            // pressure-level data (every input a field, the last one a number per segment): its own copy of the tile body, in which the
+            // compiler sees that the points of a tile share the scalar and computes what depends on it alone once per tile
+            if (vec_ok && B.in_mask == (1u << (NIN - 1)) - 1u) {
+                load_tile<Op, T, UNROLL, true, 2>(A, in, base);
+                prefetch_next();
+                compute_store_tile<Op, OpE, T, UNROLL, true>(A, out, base, P, B.in_mask);
+                continue;
+            }
+        }
         if (vec_ok && all_arrays)
             load_tile<Op, T, UNROLL, true, 1>(A, in, base);
         else if (vec_ok)
             load_tile<Op, T, UNROLL, true, 0>(A, in, base);
         else
             load_tile<Op, T, UNROLL, false, 0>(A, in, base);
-        if (Op::PREFETCH_NEXT) {  // the CTA's tile EK_PF_DIST rounds ahead, possibly in a later segment
-            const int64_t nt = tile + EK_PF_DIST * (int64_t)gridDim.x;
-            if (nt < ntiles) {
-                const int nseg = (int)(nt / tiles_per_seg);
-                InArgs<NIN> nin;
-#pragma unroll
-                for (int k = 0; k < NIN; ++k) nin.p[k] = ((B.in_mask >> k) & 1u) ? B.in[k][nseg] : nullptr;
-                prefetch_tile_l2<Op, T, UNROLL>(nin, (nt - (int64_t)nseg * tiles_per_seg) * TILE + toff);
-            }
-        }
+        prefetch_next();
         if (vec_ok)
             compute_store_tile<Op, OpE, T, UNROLL, true>(A, out, base, P, B.in_mask);
         else

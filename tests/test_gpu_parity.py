@@ -473,6 +473,8 @@ def test_batched_suite_equals_per_field_launches(ek, dtype):
     # pressure-level data: one pressure PER FIELD (150 levels: two launches, the second one starts at level 128)
     levels = [float(x) for x in np.linspace(100.0, 101325.0, n_seg)]
     levels[3] = 3.0  # p - es < 1e-4 on most points: the NaN rule
+    ts[64][::97] = float("nan")  # missing values and zeros in a field: the exact recompute inside the batched kernel
+    ts[127][5::101] = 0.0
     for outputs, em in ((("theta", "rh"), "ifs"), (fused.ALL7_TQP, "ifs"), (fused.ALL7_TQP, "bolton39")):
         got = fused.suite_tqp_batch(ts, qs, levels, outputs=outputs, ept_method=em)
         for j in (0, 3, 64, 127, 128, n_seg - 1):
